@@ -1,0 +1,500 @@
+// antialias.cu -- B200-native replacement of the reference's antialias op:
+//   antialias_construct_topology_hash (csrc/torch/torch_antialias.cpp:25-63,  csrc/common/antialias.cu:47-160)
+//   antialias_fwd                     (csrc/torch/torch_antialias.cpp:68-155, csrc/common/antialias.cu:165-382)
+//   antialias_grad                    (csrc/torch/torch_antialias.cpp:160-241, csrc/common/antialias.cu:387-556)
+//
+// Differences in structure (results are the same):
+//   * topology is a per-triangle table of the three opposite ("wing") vertices, built once through a transient edge
+//     hash; the per-pixel-pair analysis then needs one 16-byte load instead of three hash probes;
+//   * the dense pass is fused: one kernel streams color -> out (the reference clones the tensor first), compares
+//     triangle ids with the right/up neighbours and appends work items with one atomic per warp;
+//   * position gradients are summed per run of equal (triangle, edge) inside the warp before the atomics.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Topology
+
+struct EdgeSlot { unsigned long long key; int a, b; };   // 16 bytes; a, b = opposite vertex + 1 (0 = empty)
+
+static __device__ __forceinline__ unsigned long long mix64(unsigned long long x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+static __device__ __forceinline__ unsigned long long edge_key(int va, int vb)
+{
+    return (unsigned long long)(unsigned)(min(va, vb) + 1) | ((unsigned long long)(unsigned)(max(va, vb) + 1) << 32);
+}
+
+static __device__ __forceinline__ void edge_insert(EdgeSlot* tab, unsigned long long mask, int va, int vb, int vn)
+{
+    if (va == vb) return;
+    unsigned long long k = edge_key(va, vb);
+    unsigned long long i = mix64(k) & mask;
+    for (;;)
+    {
+        unsigned long long prev = atomicCAS(&tab[i].key, 0ULL, k);
+        if (prev == 0ULL || prev == k) break;
+        i = (i + 1) & mask;
+    }
+    int old = atomicCAS(&tab[i].a, 0, vn + 1);
+    if (old != 0 && old != vn + 1) atomicCAS(&tab[i].b, 0, vn + 1);     // third and later triangles on an edge are dropped
+}
+
+static __device__ __forceinline__ int edge_find(const EdgeSlot* tab, unsigned long long mask, int va, int vb, int vr)
+{
+    if (va == vb) return -1;
+    unsigned long long k = edge_key(va, vb);
+    unsigned long long i = mix64(k) & mask;
+    for (;;)
+    {
+        unsigned long long kk = tab[i].key;
+        if (kk == k || kk == 0ULL) break;
+        i = (i + 1) & mask;
+    }
+    int a = tab[i].a - 1, b = tab[i].b - 1;
+    if (a == vr) return b;
+    if (b == vr) return a;
+    return -1;
+}
+
+static __device__ __forceinline__ bool load_tri(const int32_t* tri, int t, int V, int& v0, int& v1, int& v2)
+{
+    v0 = __ldg(tri + t * 3 + 0); v1 = __ldg(tri + t * 3 + 1); v2 = __ldg(tri + t * 3 + 2);
+    return !(v0 < 0 || v0 >= V || v1 < 0 || v1 >= V || v2 < 0 || v2 >= V);
+}
+
+__global__ void __launch_bounds__(256) topology_insert_kernel(const int32_t* tri, int T, int V, EdgeSlot* tab, unsigned long long mask)
+{
+    int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= T) return;
+    int v0, v1, v2;
+    if (!load_tri(tri, t, V, v0, v1, v2)) return;
+    if (v0 == v1 || v1 == v2 || v2 == v0) return;
+    edge_insert(tab, mask, v1, v2, v0);
+    edge_insert(tab, mask, v2, v0, v1);
+    edge_insert(tab, mask, v0, v1, v2);
+}
+
+__global__ void __launch_bounds__(256) topology_wings_kernel(const int32_t* tri, int T, int V, const EdgeSlot* tab, unsigned long long mask, int4* wings)
+{
+    int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= T) return;
+    int v0, v1, v2;
+    int4 w = make_int4(-1, -1, -1, 0);
+    if (load_tri(tri, t, V, v0, v1, v2))
+    {
+        w.x = edge_find(tab, mask, v2, v1, v0);
+        w.y = edge_find(tab, mask, v0, v2, v1);
+        w.z = edge_find(tab, mask, v1, v0, v2);
+    }
+    wings[t] = w;
+}
+
+static unsigned long long topology_slots(int T)
+{
+    unsigned long long n = 64;
+    while (n < (unsigned long long)T) n <<= 1;
+    return n * 4;       // <= 3T distinct edges: load factor <= 0.75, typically < 0.4
+}
+
+// ------------------------------------------------------------------------------------------------
+// Work items.  int4: x = px | py << 16, y = pz, z = flags, w = alpha bits (0 = no blend).
+
+#define AA_FLAG_DOWN_BIT 2
+#define AA_FLAG_TRI1_BIT 3
+#define AA_EDGE_MASK     3
+
+struct AAParams
+{
+    const float* color; const float* rast; const int32_t* tri; const float* pos; const int4* wings;
+    float* out; const float* dy; float* g_color; float* g_pos;
+    int4* items; int* counters;         // counters[0] = number of items
+    int N, H, W, C, V, T, instance_mode;
+    int vec_ok;                         // color/out are 16-byte aligned
+    float xh, yh;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Dense pass: out = color, find id discontinuities (csrc/common/antialias.cu:165-214).
+
+#define AA_TILE_W 32
+#define AA_TILE_H 8
+
+__global__ void __launch_bounds__(AA_TILE_W * AA_TILE_H) aa_discontinuity_kernel(const AAParams p)
+{
+    __shared__ float s_id[AA_TILE_H + 1][AA_TILE_W];
+    const int lane = threadIdx.x, ty = threadIdx.y;
+    const int px = blockIdx.x * AA_TILE_W + lane;
+    const int py = blockIdx.y * AA_TILE_H + ty;
+    const int pz = blockIdx.z;
+    const bool inb = (px < p.W) && (py < p.H);
+    const size_t row = ((size_t)pz * p.H + min(py, p.H - 1)) * p.W;         // clamped so that address math stays valid
+
+    // ---- color -> out for this warp's row segment (contiguous floats; 128-bit when the layout allows)
+    if (py < p.H)
+    {
+        int x0 = blockIdx.x * AA_TILE_W;
+        int nflt = min(AA_TILE_W, p.W - x0) * p.C;
+        size_t base = (row + x0) * p.C;
+        if (p.vec_ok && ((p.W * p.C) & 3) == 0 && ((x0 * p.C) & 3) == 0)
+        {
+            const float4* src = (const float4*)(p.color + base);
+            float4* dst = (float4*)(p.out + base);
+            for (int i = lane; i < (nflt >> 2); i += 32) st_stream_f4(dst + i, ld_stream_f4(src + i));
+        }
+        else
+        {
+            for (int i = lane; i < nflt; i += 32) st_stream_f(p.out + base + i, ld_stream_f(p.color + base + i));
+        }
+    }
+
+    // ---- triangle ids of the tile plus the row above it
+    float tri0 = 0.f;
+    if (inb) tri0 = __ldg(p.rast + (row + px) * 4 + 3);
+    s_id[ty][lane] = tri0;
+    if (ty == AA_TILE_H - 1)
+    {
+        float up = tri0;
+        if (inb && py < p.H - 1) up = __ldg(p.rast + (row + p.W + px) * 4 + 3);
+        s_id[AA_TILE_H][lane] = up;
+    }
+    float tri1 = __shfl_down_sync(0xffffffffu, tri0, 1);                   // right neighbour
+    if (lane == 31 && inb && px < p.W - 1) tri1 = __ldg(p.rast + (row + px + 1) * 4 + 3);
+    if (!inb || px >= p.W - 1) tri1 = tri0;                                // clamp at the image edge
+    __syncthreads();
+    float tri2 = tri0;
+    if (inb && py < p.H - 1) tri2 = s_id[ty + 1][lane];                    // neighbour in the next row
+
+    // ---- append work items, one atomic per warp
+    bool f1 = inb && (tri1 != tri0), f2 = inb && (tri2 != tri0);
+    unsigned m1 = __ballot_sync(0xffffffffu, f1), m2 = __ballot_sync(0xffffffffu, f2);
+    if ((m1 | m2) == 0) return;
+    int n1 = __popc(m1), total = n1 + __popc(m2);
+    int base = 0;
+    if (lane == 0) base = atomicAdd(p.counters, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    unsigned lt = (1u << lane) - 1u;
+    int pxy = px | (py << 16);
+    if (f1) p.items[base + __popc(m1 & lt)] = make_int4(pxy, pz, 0, 0);
+    if (f2) p.items[base + n1 + __popc(m2 & lt)] = make_int4(pxy, pz, 1 << AA_FLAG_DOWN_BIT, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sparse pass: silhouette analysis and blending (csrc/common/antialias.cu:219-382).
+
+static __device__ __forceinline__ bool same_sign(float a, float b) { return (__float_as_int(a) ^ __float_as_int(b)) >= 0; }
+static __device__ __forceinline__ bool rational_gt(float n0, float n1, float d0, float d1) { return (n0 * d1 > n1 * d0) == same_sign(d0, d1); }
+static __device__ __forceinline__ int max_idx3(float n0, float n1, float n2, float d0, float d1, float d2)
+{
+    bool g10 = rational_gt(n1, n0, d1, d0);
+    bool g20 = rational_gt(n2, n0, d2, d0);
+    bool g21 = rational_gt(n2, n1, d2, d1);
+    if (g20 && g21) return 2;
+    if (g10) return 1;
+    return 0;
+}
+#define AA_F32_MAX (3.402823466e+38f)
+
+__global__ void __launch_bounds__(256) aa_analysis_kernel(const AAParams p)
+{
+    const int count = min(p.counters[0], 2 * p.N * p.H * p.W);
+    for (int idx = blockIdx.x * 256 + threadIdx.x; idx < count; idx += gridDim.x * 256)
+    {
+        int4 item = p.items[idx];
+        int px = item.x & 0xFFFF, py = (int)((unsigned)item.x >> 16), pz = item.y;
+        int d = (item.z >> AA_FLAG_DOWN_BIT) & 1;
+
+        int pixel0 = px + p.W * (py + p.H * pz);
+        int pixel1 = pixel0 + (d ? p.W : 1);
+        float2 zt0 = __ldg((const float2*)p.rast + ((size_t)pixel0 << 1) + 1);
+        float2 zt1 = __ldg((const float2*)p.rast + ((size_t)pixel1 << 1) + 1);
+        int tri0 = float_to_triidx(zt0.y) - 1;
+        int tri1 = float_to_triidx(zt1.y) - 1;
+
+        // nearer of the two surfaces (background loses)
+        int tri = (tri0 >= 0) ? tri0 : tri1;
+        if (tri0 >= 0 && tri1 >= 0) tri = (zt0.x < zt1.x) ? tri0 : tri1;
+        if (tri == tri1) { px += 1 - d; py += d; }
+        if (tri < 0 || tri >= p.T) continue;
+
+        int vi0, vi1, vi2;
+        if (!load_tri(p.tri, tri, p.V, vi0, vi1, vi2)) continue;
+        int4 wg = __ldg(p.wings + tri);
+        int op0 = wg.x, op1 = wg.y, op2 = wg.z;
+        if (p.instance_mode)
+        {
+            int vbase = pz * p.V;
+            vi0 += vbase; vi1 += vbase; vi2 += vbase;
+            if (op0 >= 0) op0 += vbase;
+            if (op1 >= 0) op1 += vbase;
+            if (op2 >= 0) op2 += vbase;
+        }
+        const float4* vb = (const float4*)p.pos;
+        float4 p0 = __ldg(vb + vi0), p1 = __ldg(vb + vi1), p2 = __ldg(vb + vi2);
+        float4 o0 = (op0 < 0) ? p0 : __ldg(vb + op0);
+        float4 o1 = (op1 < 0) ? p1 : __ldg(vb + op1);
+        float4 o2 = (op2 < 0) ? p2 : __ldg(vb + op2);
+
+        // to pixel space, relative to the chosen pixel's centre
+        float w0 = 1.f / p0.w, w1 = 1.f / p1.w, w2 = 1.f / p2.w;
+        float ow0 = 1.f / o0.w, ow1 = 1.f / o1.w, ow2 = 1.f / o2.w;
+        float fx = (float)px + .5f - p.xh;
+        float fy = (float)py + .5f - p.yh;
+        float x0 = p0.x * w0 * p.xh - fx, y0 = p0.y * w0 * p.yh - fy;
+        float x1 = p1.x * w1 * p.xh - fx, y1 = p1.y * w1 * p.yh - fy;
+        float x2 = p2.x * w2 * p.xh - fx, y2 = p2.y * w2 * p.yh - fy;
+        float ox0 = o0.x * ow0 * p.xh - fx, oy0 = o0.y * ow0 * p.yh - fy;
+        float ox1 = o1.x * ow1 * p.xh - fx, oy1 = o1.y * ow1 * p.yh - fy;
+        float ox2 = o2.x * ow2 * p.xh - fx, oy2 = o2.y * ow2 * p.yh - fy;
+
+        // silhouette test: a wing on the same side as the triangle itself
+        float bb = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
+        float a0 = (x1 - ox0) * (y2 - oy0) - (x2 - ox0) * (y1 - oy0);
+        float a1 = (x2 - ox1) * (y0 - oy1) - (x0 - ox1) * (y2 - oy1);
+        float a2 = (x0 - ox2) * (y1 - oy2) - (x1 - ox2) * (y0 - oy2);
+        if (!(same_sign(a0, bb) || same_sign(a1, bb) || same_sign(a2, bb))) continue;
+
+        if (d) { float t; t = x0; x0 = y0; y0 = t; t = x1; x1 = y1; y1 = t; t = x2; x2 = y2; y2 = t; }
+        float dx0 = x2 - x1, dx1 = x0 - x2, dx2 = x1 - x0;
+        float dy0 = y2 - y1, dy1 = y0 - y2, dy2 = y1 - y0;
+
+        float dc = -AA_F32_MAX;
+        float ds = (tri == tri0) ? 1.f : -1.f;
+        float d0 = ds * (x1 * dy0 - y1 * dx0);
+        float d1 = ds * (x2 * dy1 - y2 * dx1);
+        float d2 = ds * (x0 * dy2 - y0 * dx2);
+        if (same_sign(y1, y2)) { d0 = -AA_F32_MAX; dy0 = 1.f; }
+        if (same_sign(y2, y0)) { d1 = -AA_F32_MAX; dy1 = 1.f; }
+        if (same_sign(y0, y1)) { d2 = -AA_F32_MAX; dy2 = 1.f; }
+
+        int di = max_idx3(d0, d1, d2, dy0, dy1, dy2);
+        if (di == 0 && same_sign(a0, bb) && fabsf(dy0) >= fabsf(dx0)) dc = d0 / dy0;
+        if (di == 1 && same_sign(a1, bb) && fabsf(dy1) >= fabsf(dx1)) dc = d1 / dy1;
+        if (di == 2 && same_sign(a2, bb) && fabsf(dy2) >= fabsf(dx2)) dc = d2 / dy2;
+        const float eps = .0625f;
+
+        if (dc > -eps && dc < 1.f + eps)
+        {
+            dc = fminf(fmaxf(dc, 0.f), 1.f);
+            float alpha = ds * (.5f - dc);
+            const float* c0 = p.color + (size_t)pixel0 * p.C;
+            const float* c1 = p.color + (size_t)pixel1 * p.C;
+            float* o = p.out + (size_t)(alpha > 0.f ? pixel0 : pixel1) * p.C;
+            for (int i = 0; i < p.C; i++) red_add(o + i, alpha * (__ldg(c1 + i) - __ldg(c0 + i)));
+
+            unsigned flags = (unsigned)di | ((unsigned)d << AA_FLAG_DOWN_BIT) | ((__float_as_uint(ds) >> 31) << AA_FLAG_TRI1_BIT);
+            ((int2*)(p.items + idx))[1] = make_int2((int)flags, __float_as_int(alpha));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward (csrc/common/antialias.cu:387-556).
+
+__global__ void __launch_bounds__(256) aa_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n)
+{
+    size_t n4 = n >> 2;
+    const float4* s4 = (const float4*)src; float4* d4 = (float4*)dst;
+    size_t stride = (size_t)gridDim.x * 256;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) st_stream_f4(d4 + i, ld_stream_f4(s4 + i));
+    size_t i = (n4 << 2) + (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256) aa_grad_kernel(const AAParams p)
+{
+    const int count = min(p.counters[0], 2 * p.N * p.H * p.W);
+    const int rounds = (count + gridDim.x * 256 - 1) / (gridDim.x * 256);
+    for (int r = 0; r < rounds; r++)                   // whole warps iterate together (warp collectives below)
+    {
+        int idx = (r * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
+        int4 item = (idx < count) ? p.items[idx] : make_int4(0, 0, 0, 0);
+        bool active = (idx < count) && (item.w != 0);
+
+        int px = item.x & 0xFFFF, py = (int)((unsigned)item.x >> 16), pz = item.y;
+        int d = (item.z >> AA_FLAG_DOWN_BIT) & 1;
+        float alpha = __int_as_float(item.w);
+        int tri1f = (item.z >> AA_FLAG_TRI1_BIT) & 1;
+        int di = item.z & AA_EDGE_MASK;
+        int pixel0 = px + p.W * (py + p.H * pz);
+        int pixel1 = pixel0 + (d ? p.W : 1);
+        int tri = -1;
+        if (active)
+        {
+            tri = float_to_triidx(__ldg(p.rast + ((size_t)(tri1f ? pixel1 : pixel0) << 2) + 3)) - 1;
+            if (tri < 0 || tri >= p.T) active = false;
+        }
+        if (tri1f) { px += 1 - d; py += d; }
+
+        float dd = 0.f;
+        if (active)
+        {
+            float* g0 = p.g_color + (size_t)pixel0 * p.C;
+            float* g1 = p.g_color + (size_t)pixel1 * p.C;
+            const float* pdy = p.dy + (size_t)(alpha > 0.f ? pixel0 : pixel1) * p.C;
+            const float* c0 = p.color + (size_t)pixel0 * p.C;
+            const float* c1 = p.color + (size_t)pixel1 * p.C;
+            for (int i = 0; i < p.C; i++)
+            {
+                float dy = __ldg(pdy + i);
+                if (dy != 0.f)
+                {
+                    dd += dy * (__ldg(c1 + i) - __ldg(c0 + i));
+                    float v = alpha * dy;
+                    red_add(g0 + i, -v);
+                    red_add(g1 + i, v);
+                }
+            }
+            if (dd == 0.f) active = false;
+        }
+
+        int vi1 = 0, vi2 = 0;
+        if (active)
+        {
+            int i1 = (di < 2) ? (di + 1) : 0;
+            int i2 = (i1 < 2) ? (i1 + 1) : 0;
+            vi1 = __ldg(p.tri + 3 * tri + i1);
+            vi2 = __ldg(p.tri + 3 * tri + i2);
+            if (vi1 < 0 || vi1 >= p.V || vi2 < 0 || vi2 >= p.V) active = false;
+            else if (p.instance_mode) { vi1 += pz * p.V; vi2 += pz * p.V; }
+        }
+
+        float g[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
+        if (active)
+        {
+            float4 p1 = __ldg((const float4*)p.pos + vi1);
+            float4 p2 = __ldg((const float4*)p.pos + vi2);
+            float pxh = p.xh, pyh = p.yh;
+            float fx = (float)px + .5f - pxh;
+            float fy = (float)py + .5f - pyh;
+            if (d)
+            {
+                float t;
+                t = p1.x; p1.x = p1.y; p1.y = t;
+                t = p2.x; p2.x = p2.y; p2.y = t;
+                t = pxh; pxh = pyh; pyh = t;
+                t = fx; fx = fy; fy = t;
+            }
+            float w1 = 1.f / p1.w, w2 = 1.f / p2.w;
+            float x1 = p1.x * w1 * pxh - fx, y1 = p1.y * w1 * pyh - fy;
+            float x2 = p2.x * w2 * pxh - fx, y2 = p2.y * w2 * pyh - fy;
+            float dx = x2 - x1, dy = y2 - y1;
+            float db = x1 * dy - y1 * dx;
+
+            float ep = copysignf(1e-3f, dy);
+            float iy = 1.f / (dy + ep);
+            float dby = db * iy;
+            float iw1 = -w1 * iy * dd;
+            float iw2 =  w2 * iy * dd;
+            float gp1x = iw1 * pxh * y2;
+            float gp2x = iw2 * pxh * y1;
+            float gp1y = iw1 * pyh * (dby - x2);
+            float gp2y = iw2 * pyh * (dby - x1);
+            float gp1w = -(p1.x * gp1x + p1.y * gp1y) * w1;
+            float gp2w = -(p2.x * gp2x + p2.y * gp2y) * w2;
+            if (d) { float t; t = gp1x; gp1x = gp1y; gp1y = t; t = gp2x; gp2x = gp2y; gp2y = t; }
+            if (fabsf(alpha) >= 0.5f) { gp1x = gp1y = gp1w = 0.f; gp2x = gp2y = gp2w = 0.f; }
+            g[0] = gp1x; g[1] = gp1y; g[2] = gp1w; g[3] = gp2x; g[4] = gp2y; g[5] = gp2w;
+        }
+
+        // consecutive items often hit the same edge (same two vertices): sum such runs before the atomics
+        if (__any_sync(0xffffffffu, active))
+        {
+            WarpRuns runs = warp_runs2(active ? vi1 : -1, active ? vi2 : -1);
+            #pragma unroll
+            for (int i = 0; i < 6; i++) g[i] = warp_run_sum(g[i], runs);
+            if (runs.is_head && active)
+            {
+                float* q1 = p.g_pos + 4 * (size_t)vi1; float* q2 = p.g_pos + 4 * (size_t)vi2;
+                red_add(q1 + 0, g[0]); red_add(q1 + 1, g[1]); red_add(q1 + 3, g[2]);
+                red_add(q2 + 0, g[3]); red_add(q2 + 1, g[4]); red_add(q2 + 3, g[5]);
+            }
+        }
+    }
+}
+
+static int aa_fill(AAParams& p, const char* fn, const float* color, const float* rast, const float* pos, const int32_t* tri,
+                   int N, int H, int W, int C, int V, int T, int instance_mode)
+{
+    B200DR_CHECK(N > 0 && H > 0 && W > 0 && C > 0, "%s: color must have shape[>0, >0, >0, >0]", fn);
+    B200DR_CHECK(V > 0 && T > 0, "%s: pos/tri must be non-empty", fn);
+    B200DR_CHECK(H < 65536 && W < 65536 && N <= 65535, "%s: image size or minibatch too large", fn);
+    B200DR_CHECK((size_t)N * H * W < (1ull << 30), "%s: too many pixels for 32-bit work indexing", fn);
+    B200DR_CHECK(B200DR_ALIGNED16(pos), "%s: pos input tensor not aligned to float4", fn);
+    B200DR_CHECK((((uintptr_t)rast) & 7) == 0, "%s: raster_out input tensor not aligned to float2", fn);
+    p.color = color; p.rast = rast; p.pos = pos; p.tri = tri;
+    p.N = N; p.H = H; p.W = W; p.C = C; p.V = V; p.T = T; p.instance_mode = instance_mode;
+    p.xh = .5f * (float)W; p.yh = .5f * (float)H;
+    return 0;
+}
+
+} // namespace
+
+extern "C" size_t b200dr_topology_scratch_bytes(int T)
+{
+    return (size_t)topology_slots(T) * sizeof(EdgeSlot);
+}
+
+extern "C" int b200dr_antialias_construct_topology(const int32_t* tri, int T, int V, int32_t* wings,
+                                                   void* scratch, size_t scratch_bytes, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B200DR_CHECK(T > 0, "antialias_construct_topology_hash(): tri must have shape [>0, 3]");
+    B200DR_CHECK(scratch && scratch_bytes >= b200dr_topology_scratch_bytes(T), "antialias_construct_topology_hash(): scratch buffer too small");
+    B200DR_CHECK(B200DR_ALIGNED16(scratch) && B200DR_ALIGNED16(wings), "antialias_construct_topology_hash(): internal tensor not aligned to int4");
+    unsigned long long slots = topology_slots(T);
+    cudaMemsetAsync(scratch, 0, slots * sizeof(EdgeSlot), stream);
+    int blocks = (T + 255) / 256;
+    topology_insert_kernel<<<blocks, 256, 0, stream>>>(tri, T, V, (EdgeSlot*)scratch, slots - 1);
+    topology_wings_kernel<<<blocks, 256, 0, stream>>>(tri, T, V, (const EdgeSlot*)scratch, slots - 1, (int4*)wings);
+    b200dr_count_launches(1);   // two kernels, one check below
+    B200DR_CHECK_LAUNCH("antialias_construct_topology_hash()");
+    return 0;
+}
+
+extern "C" int b200dr_antialias_fwd(const float* color, const float* rast, const float* pos, const int32_t* tri, const int32_t* wings,
+                                    int N, int H, int W, int C, int V, int T, int instance_mode,
+                                    float* out, void* work_items, int32_t* work_counters, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AAParams p = {};
+    if (aa_fill(p, "antialias_fwd()", color, rast, pos, tri, N, H, W, C, V, T, instance_mode)) return 1;
+    B200DR_CHECK(B200DR_ALIGNED16(work_items), "antialias_fwd(): work_buffer internal tensor not aligned to int4");
+    p.wings = (const int4*)wings; p.out = out; p.vec_ok = B200DR_ALIGNED16(color) && B200DR_ALIGNED16(out); p.items = (int4*)work_items; p.counters = work_counters;
+    cudaMemsetAsync(work_counters, 0, 4 * sizeof(int), stream);
+    dim3 grid((W + AA_TILE_W - 1) / AA_TILE_W, (H + AA_TILE_H - 1) / AA_TILE_H, N);
+    aa_discontinuity_kernel<<<grid, dim3(AA_TILE_W, AA_TILE_H), 0, stream>>>(p);
+    B200DR_CHECK_LAUNCH("antialias_fwd(discontinuity)");
+    aa_analysis_kernel<<<b200dr_num_sms() * 8, 256, 0, stream>>>(p);
+    B200DR_CHECK_LAUNCH("antialias_fwd(analysis)");
+    return 0;
+}
+
+extern "C" int b200dr_antialias_grad(const float* color, const float* rast, const float* pos, const int32_t* tri, const float* dy,
+                                     const void* work_items, const int32_t* work_counters,
+                                     int N, int H, int W, int C, int V, int T, int instance_mode,
+                                     float* g_color, float* g_pos, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AAParams p = {};
+    if (aa_fill(p, "antialias_grad()", color, rast, pos, tri, N, H, W, C, V, T, instance_mode)) return 1;
+    p.dy = dy; p.g_color = g_color; p.g_pos = g_pos; p.items = (int4*)work_items; p.counters = (int*)work_counters;
+    size_t n = (size_t)N * H * W * C;
+    if (B200DR_ALIGNED16(dy) && B200DR_ALIGNED16(g_color))
+    {
+        size_t blocks = ((n >> 2) + 255) / 256;
+        size_t cap = (size_t)b200dr_num_sms() * 32;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        aa_copy_kernel<<<(unsigned)blocks, 256, 0, stream>>>(dy, g_color, n);
+        B200DR_CHECK_LAUNCH("antialias_grad(copy)");
+    }
+    else
+        cudaMemcpyAsync(g_color, dy, n * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+    aa_grad_kernel<<<b200dr_num_sms() * 8, 256, 0, stream>>>(p);
+    B200DR_CHECK_LAUNCH("antialias_grad()");
+    return 0;
+}

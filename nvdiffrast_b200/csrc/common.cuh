@@ -1,0 +1,185 @@
+// Shared device/host helpers for libb200dr (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "b200dr.h"
+
+// ------------------------------------------------------------------------------------------------
+// Host-side error plumbing (C ABI returns int, message kept thread-local).
+
+void b200dr_set_error(const char* fmt, ...);
+
+#define B200DR_CHECK(cond, ...)                                        \
+    do { if (!(cond)) { b200dr_set_error(__VA_ARGS__); return 1; } } while (0)
+
+#define B200DR_CHECK_LAUNCH(name)                                                            \
+    do { b200dr_count_launches(1); cudaError_t e_ = cudaGetLastError();                                               \
+         if (e_ != cudaSuccess) { b200dr_set_error("%s: Cuda error: %s", name, cudaGetErrorString(e_)); return 1; } } while (0)
+
+#define B200DR_ALIGNED16(p) ((((uintptr_t)(p)) & 15) == 0)
+
+void b200dr_count_launches(int n);
+
+// B200: 148 SMs.  Queried once per device at first use.
+int b200dr_num_sms(void);
+
+#ifdef __CUDACC__
+
+// ------------------------------------------------------------------------------------------------
+// Constants shared with the oracle (csrc/common/cudaraster/impl/Constants.hpp:69-71).
+
+#define DR_DEPTH_MIN 17600u
+#define DR_DEPTH_MAX (0xFFFFFFFFu - 17600u)
+
+// ------------------------------------------------------------------------------------------------
+// Triangle id <-> float codec (csrc/common/common.h:192-193).
+
+static __device__ __forceinline__ int   float_to_triidx(float x) { if (x <= 16777216.f) return (int)x; return __float_as_int(x) - 0x4a800000; }
+static __device__ __forceinline__ float triidx_to_float(int x)   { if (x <= 0x01000000) return (float)x; return __int_as_float(0x4a800000 + x); }
+
+// ------------------------------------------------------------------------------------------------
+// Streaming loads / stores.  Per-pixel tensors are touched exactly once per kernel: keep them out of L1
+// (L2::evict_first needs 256-bit accesses on sm_100a; plain no_allocate is used here).
+
+static __device__ __forceinline__ float4 ld_stream_f4(const float4* p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+static __device__ __forceinline__ float2 ld_stream_f2(const float2* p)
+{
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+static __device__ __forceinline__ float ld_stream_f(const float* p)
+{
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+static __device__ __forceinline__ void st_stream_f4(float4* p, float4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+static __device__ __forceinline__ void st_stream_f2(float2* p, float2 v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" :: "l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+static __device__ __forceinline__ void st_stream_f(float* p, float v)
+{
+    asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+static __device__ __forceinline__ void st_stream_u4(uint4* p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-level segmented ("run") reduction.
+//
+// Gradient kernels see 32 consecutive pixels per warp; pixels of one triangle form runs.  Instead of one atomic
+// per pixel per value (or the reference's __match_any + shared-memory atomics, csrc/common/common.h:198-241),
+// every run is summed with 5 shuffles and only the run's head lane issues the atomic.
+
+struct WarpRuns
+{
+    unsigned heads;     // bit l set: lane l starts a run
+    int      run_end;   // first lane after this lane's run (1..32)
+    bool     is_head;
+};
+
+// key: any int identifying the group of a lane (all lanes of the warp must call).
+static __device__ __forceinline__ WarpRuns warp_runs(int key)
+{
+    const int lane = threadIdx.x & 31;
+    int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    bool head = (lane == 0) || (prev != key);
+    WarpRuns r;
+    r.heads = __ballot_sync(0xffffffffu, head);
+    unsigned above = (lane == 31) ? 0u : (r.heads >> (lane + 1));
+    r.run_end = above ? (lane + __ffs(above)) : 32;
+    r.is_head = head;
+    return r;
+}
+
+// Same, runs of equal (key0, key1) pairs.
+static __device__ __forceinline__ WarpRuns warp_runs2(int key0, int key1)
+{
+    const int lane = threadIdx.x & 31;
+    int prev0 = __shfl_up_sync(0xffffffffu, key0, 1);
+    int prev1 = __shfl_up_sync(0xffffffffu, key1, 1);
+    bool head = (lane == 0) || (prev0 != key0) || (prev1 != key1);
+    WarpRuns r;
+    r.heads = __ballot_sync(0xffffffffu, head);
+    unsigned above = (lane == 31) ? 0u : (r.heads >> (lane + 1));
+    r.run_end = above ? (lane + __ffs(above)) : 32;
+    r.is_head = head;
+    return r;
+}
+
+// Sum v over each run; the result is valid in the run's head lane.
+static __device__ __forceinline__ float warp_run_sum(float v, const WarpRuns& r)
+{
+    const int lane = threadIdx.x & 31;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        float t = __shfl_down_sync(0xffffffffu, v, d);
+        if (lane + d < r.run_end) v += t;
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-cooperative staging copies (all streaming kernels run DR_THREADS threads per CTA).
+
+#define DR_THREADS 256
+
+// Cooperative copy of n contiguous floats shared -> global.  Uses 128-bit stores on the 16-byte aligned body.
+static __device__ __forceinline__ void coop_store(float* __restrict__ g, const float* __restrict__ s, int n, int tid)
+{
+    int head = (int)(((16 - ((uintptr_t)g & 15)) & 15) >> 2);
+    if (head > n) head = n;
+    if (tid < head) st_stream_f(g + tid, s[tid]);
+    int body = (n - head) >> 2;
+    float4* g4 = (float4*)(g + head);
+    for (int i = tid; i < body; i += DR_THREADS)
+    {
+        const float* q = s + head + 4 * i;
+        st_stream_f4(g4 + i, make_float4(q[0], q[1], q[2], q[3]));
+    }
+    int done = head + 4 * body;
+    if (tid < n - done) st_stream_f(g + done + tid, s[done + tid]);
+}
+
+// Cooperative copy of n contiguous floats global -> shared (128-bit loads on the aligned body).
+static __device__ __forceinline__ void coop_load(float* __restrict__ s, const float* __restrict__ g, int n, int tid)
+{
+    int head = (int)(((16 - ((uintptr_t)g & 15)) & 15) >> 2);
+    if (head > n) head = n;
+    if (tid < head) s[tid] = ld_stream_f(g + tid);
+    int body = (n - head) >> 2;
+    const float4* g4 = (const float4*)(g + head);
+    for (int i = tid; i < body; i += DR_THREADS)
+    {
+        float4 v = ld_stream_f4(g4 + i);
+        float* q = s + head + 4 * i;
+        q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+    }
+    int done = head + 4 * body;
+    if (tid < n - done) s[done + tid] = ld_stream_f(g + done + tid);
+}
+
+// fp32 add without return value (RED).  Works on shared and global addresses.
+static __device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
+// 128-bit vector reduction (global memory only, 16-byte aligned): REDG.E.ADD.F32x4 on sm_100a.
+static __device__ __forceinline__ void red_add4(float* p, float4 v)
+{
+    asm volatile("red.global.v4.f32.add [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+#endif // __CUDACC__

@@ -1,0 +1,347 @@
+// interpolate.cu -- B200-native replacement of the reference's interpolate op:
+//   interpolate_fwd[_da]  (csrc/torch/torch_interpolate.cpp:42-132,  csrc/common/interpolate.cu:15-126)
+//   interpolate_grad[_da] (csrc/torch/torch_interpolate.cpp:137-248, csrc/common/interpolate.cu:131-274)
+//
+// Layout: the image batch is one flat array of P = N*H*W pixels; a warp owns 32 consecutive pixels, a CTA step
+// owns 256.  Per-pixel AoS tensors with an arbitrary channel count A ([.., A] floats) are staged through shared
+// memory so that every global access is a full-line 128-bit transaction regardless of A (the reference issues
+// 4-byte stores with stride 4A from 8-pixel rows).  Vertex-attribute gradients are summed per run of equal
+// triangle ids inside the warp (5 shuffles), accumulated in a per-CTA shared-memory copy of the gradient tensor when
+// it fits, and flushed with one atomic per touched element per CTA.
+#include "common.cuh"
+
+namespace {
+
+#define IP_THREADS DR_THREADS
+#define IP_MAX_DIFF 32      // csrc/common/interpolate.h:18
+
+struct InterpParams
+{
+    const int32_t* tri; const float* attr; const float* rast; const float* rast_db; const float* dy; const float* dda;
+    float* out; float* out_da; float* g_attr; float* g_rast; float* g_rast_db;
+    int N, H, W, V, T, A, D;
+    int attr_bc, instance_mode, diff_all;
+    int staged;             // 1: per-pixel channel tensors go through shared-memory staging
+    int use_smem_acc;       // backward: 1 = accumulate g_attr in shared memory
+    int chunks;             // 256-pixel chunks per image
+    int diff[IP_MAX_DIFF];
+};
+
+static __device__ __forceinline__ int diff_index(const InterpParams& p, int i)
+{
+    int j = p.diff_all ? i : p.diff[i];
+    if (j < 0) j += p.A;
+    return j;
+}
+
+// Decode the triangle of a pixel and fetch its (validated, instance-adjusted) vertex indices.
+static __device__ __forceinline__ bool pixel_triangle(const InterpParams& p, float idf, int n, int& vi0, int& vi1, int& vi2)
+{
+    int triIdx = float_to_triidx(idf) - 1;
+    if (triIdx < 0 || triIdx >= p.T) return false;
+    vi0 = __ldg(p.tri + triIdx * 3 + 0); vi1 = __ldg(p.tri + triIdx * 3 + 1); vi2 = __ldg(p.tri + triIdx * 3 + 2);
+    if (vi0 < 0 || vi0 >= p.V || vi1 < 0 || vi1 >= p.V || vi2 < 0 || vi2 >= p.V) return false;
+    if (p.instance_mode && !p.attr_bc) { vi0 += n * p.V; vi1 += n * p.V; vi2 += n * p.V; }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward
+
+template <bool DA>
+__global__ void __launch_bounds__(IP_THREADS) interpolate_fwd_kernel(const InterpParams p)
+{
+    extern __shared__ float s_mem[];
+    float* s_out = s_mem;                                   // [256 * A]
+    float* s_da = s_mem + IP_THREADS * p.A;                 // [256 * 2D]
+    const int tid = threadIdx.x;
+    const int n = blockIdx.y;
+    const size_t hw = (size_t)p.H * p.W;
+    const int A = p.A, D2 = 2 * p.D;
+
+    for (int c = blockIdx.x; c < p.chunks; c += gridDim.x)
+    {
+        size_t r0 = (size_t)c * IP_THREADS;
+        int npx = (int)min((size_t)IP_THREADS, hw - r0);
+        size_t pbase = (size_t)n * hw + r0;
+        bool inb = tid < npx;
+
+        float* o = p.staged ? (s_out + tid * A) : (p.out + (pbase + tid) * A);
+        float* oda = DA ? (p.staged ? (s_da + tid * D2) : (p.out_da + (pbase + tid) * D2)) : 0;
+
+        if (inb)
+        {
+            float4 r = ld_stream_f4((const float4*)p.rast + pbase + tid);
+            int vi0, vi1, vi2;
+            if (pixel_triangle(p, r.w, n, vi0, vi1, vi2))
+            {
+                const float* a0 = p.attr + (size_t)vi0 * A;
+                const float* a1 = p.attr + (size_t)vi1 * A;
+                const float* a2 = p.attr + (size_t)vi2 * A;
+                float b0 = r.x, b1 = r.y, b2 = 1.f - r.x - r.y;
+                for (int i = 0; i < A; i++)
+                    o[i] = b0 * __ldg(a0 + i) + b1 * __ldg(a1 + i) + b2 * __ldg(a2 + i);
+                if (DA)
+                {
+                    float4 db = ld_stream_f4((const float4*)p.rast_db + pbase + tid);
+                    for (int i = 0; i < p.D; i++)
+                    {
+                        int j = diff_index(p, i);
+                        float dsdx = 0.f, dsdy = 0.f;
+                        if (j >= 0 && j < A)
+                        {
+                            float s2 = __ldg(a2 + j);
+                            float dsdu = __ldg(a0 + j) - s2;
+                            float dsdv = __ldg(a1 + j) - s2;
+                            dsdx = db.x * dsdu + db.z * dsdv;
+                            dsdy = db.y * dsdu + db.w * dsdv;
+                        }
+                        oda[2 * i] = dsdx; oda[2 * i + 1] = dsdy;
+                    }
+                }
+            }
+            else
+            {
+                for (int i = 0; i < A; i++) o[i] = 0.f;
+                if (DA) for (int i = 0; i < D2; i++) oda[i] = 0.f;
+            }
+        }
+
+        if (p.staged)
+        {
+            __syncthreads();
+            coop_store(p.out + pbase * A, s_out, npx * A, tid);
+            if (DA) coop_store(p.out_da + pbase * D2, s_da, npx * D2, tid);
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward
+
+template <bool DA>
+__global__ void __launch_bounds__(IP_THREADS) interpolate_grad_kernel(const InterpParams p)
+{
+    extern __shared__ float s_mem[];
+    const int tid = threadIdx.x;
+    const int n = blockIdx.y;
+    const size_t hw = (size_t)p.H * p.W;
+    const int A = p.A, D2 = 2 * p.D;
+    const bool per_image = p.instance_mode && !p.attr_bc;
+    const int acc_n = p.V * A;
+
+    float* gbase = p.g_attr + (per_image ? (size_t)n * acc_n : 0);
+    float* s_acc = s_mem;                                           // [V*A] when use_smem_acc
+    float* s_dy = s_mem + (p.use_smem_acc ? acc_n : 0);             // [256*A]
+    float* s_dda = s_dy + (p.staged ? IP_THREADS * A : 0);          // [256*2D]
+    float* acc = p.use_smem_acc ? s_acc : p.g_attr;                 // global mode: vertex ids already carry the image offset
+    const int voff = (p.use_smem_acc && per_image) ? n * p.V : 0;   // shared copy is indexed by image-local vertex id
+
+    if (p.use_smem_acc)
+    {
+        for (int i = tid; i < acc_n; i += IP_THREADS) s_acc[i] = 0.f;
+        __syncthreads();
+    }
+
+    for (int c = blockIdx.x; c < p.chunks; c += gridDim.x)
+    {
+        size_t r0 = (size_t)c * IP_THREADS;
+        int npx = (int)min((size_t)IP_THREADS, hw - r0);
+        size_t pbase = (size_t)n * hw + r0;
+        bool inb = tid < npx;
+
+        if (p.staged)
+        {
+            coop_load(s_dy, p.dy + pbase * A, npx * A, tid);
+            if (DA) coop_load(s_dda, p.dda + pbase * D2, npx * D2, tid);
+            __syncthreads();
+        }
+        const float* pdy = p.staged ? (s_dy + tid * A) : (p.dy + (pbase + tid) * A);
+        const float* pdda = DA ? (p.staged ? (s_dda + tid * D2) : (p.dda + (pbase + tid) * D2)) : 0;
+
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        int vi0 = 0, vi1 = 0, vi2 = 0;
+        bool valid = false;
+        int key = -1;
+        if (inb)
+        {
+            r = ld_stream_f4((const float4*)p.rast + pbase + tid);
+            valid = pixel_triangle(p, r.w, n, vi0, vi1, vi2);
+            if (valid) key = float_to_triidx(r.w);
+        }
+
+        if (__any_sync(0xffffffffu, valid))
+        {
+            WarpRuns runs = warp_runs(key);
+            bool head = runs.is_head && valid;
+            const float* a0 = p.attr + (size_t)vi0 * A;     // vi* are 0 for invalid lanes: loads stay in bounds
+            const float* a1 = p.attr + (size_t)vi1 * A;
+            const float* a2 = p.attr + (size_t)vi2 * A;
+            float* ga0 = acc + (size_t)(vi0 - voff) * A;
+            float* ga1 = acc + (size_t)(vi1 - voff) * A;
+            float* ga2 = acc + (size_t)(vi2 - voff) * A;
+            float b0 = r.x, b1 = r.y, b2 = 1.f - r.x - r.y;
+            float gb0 = 0.f, gb1 = 0.f;
+            float4 db = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (DA && valid) db = ld_stream_f4((const float4*)p.rast_db + pbase + tid);
+            const bool merged = DA && p.diff_all;           // differentials of attribute i ride along with attribute i
+            float gdudx = 0.f, gdudy = 0.f, gdvdx = 0.f, gdvdy = 0.f;
+
+            for (int i = 0; i < A; i++)
+            {
+                float y = valid ? pdy[i] : 0.f;
+                float s0 = __ldg(a0 + i), s1 = __ldg(a1 + i), s2 = __ldg(a2 + i);
+                gb0 += y * (s0 - s2);
+                gb1 += y * (s1 - s2);
+                float t0 = b0 * y, t1 = b1 * y, t2 = b2 * y;
+                if (merged)
+                {
+                    float dsdx = valid ? pdda[2 * i] : 0.f, dsdy = valid ? pdda[2 * i + 1] : 0.f;
+                    float dsdu = s0 - s2, dsdv = s1 - s2;
+                    gdudx += dsdu * dsdx; gdudy += dsdu * dsdy; gdvdx += dsdv * dsdx; gdvdy += dsdv * dsdy;
+                    float du = dsdx * db.x + dsdy * db.y;
+                    float dv = dsdx * db.z + dsdy * db.w;
+                    t0 += du; t1 += dv; t2 += -du - dv;
+                }
+                t0 = warp_run_sum(t0, runs); t1 = warp_run_sum(t1, runs); t2 = warp_run_sum(t2, runs);
+                if (head) { red_add(ga0 + i, t0); red_add(ga1 + i, t1); red_add(ga2 + i, t2); }
+            }
+            if (DA && !merged)
+            {
+                for (int i = 0; i < p.D; i++)
+                {
+                    int j = diff_index(p, i);
+                    if (j < 0 || j >= A) continue;                  // uniform across the warp
+                    float dsdx = valid ? pdda[2 * i] : 0.f, dsdy = valid ? pdda[2 * i + 1] : 0.f;
+                    float s2 = __ldg(a2 + j);
+                    float dsdu = __ldg(a0 + j) - s2, dsdv = __ldg(a1 + j) - s2;
+                    gdudx += dsdu * dsdx; gdudy += dsdu * dsdy; gdvdx += dsdv * dsdx; gdvdy += dsdv * dsdy;
+                    float du = dsdx * db.x + dsdy * db.y;
+                    float dv = dsdx * db.z + dsdy * db.w;
+                    float t0 = warp_run_sum(du, runs), t1 = warp_run_sum(dv, runs), t2 = warp_run_sum(-du - dv, runs);
+                    if (head) { red_add(ga0 + j, t0); red_add(ga1 + j, t1); red_add(ga2 + j, t2); }
+                }
+            }
+            if (inb)
+            {
+                st_stream_f4((float4*)p.g_rast + pbase + tid, valid ? make_float4(gb0, gb1, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f));
+                if (DA) st_stream_f4((float4*)p.g_rast_db + pbase + tid, valid ? make_float4(gdudx, gdudy, gdvdx, gdvdy) : make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+        }
+        else if (inb)
+        {
+            st_stream_f4((float4*)p.g_rast + pbase + tid, make_float4(0.f, 0.f, 0.f, 0.f));
+            if (DA) st_stream_f4((float4*)p.g_rast_db + pbase + tid, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        if (p.staged) __syncthreads();      // staging buffers are reused by the next chunk
+    }
+
+    if (p.use_smem_acc)
+    {
+        __syncthreads();
+        for (int i = tid; i < acc_n; i += IP_THREADS)
+        {
+            float v = s_acc[i];
+            if (v != 0.f) red_add(gbase + i, v);
+        }
+    }
+}
+
+static int fill_params(InterpParams& p, const char* fn, const float* attr, const float* rast, const int32_t* tri, const float* rast_db,
+                       int N, int H, int W, int V, int T, int A, int attr_bc, int instance_mode,
+                       int diff_all, const int32_t* diff_list, int n_diff)
+{
+    B200DR_CHECK(N > 0 && H > 0 && W > 0, "%s: rast must have shape[>0, >0, >0, 4]", fn);
+    B200DR_CHECK(V > 0 && A > 0, "%s: attr must have shape [>0, >0] or [>0, >0, >0]", fn);
+    B200DR_CHECK(T > 0, "%s: tri must have shape [>0, 3]", fn);
+    B200DR_CHECK(N <= 65535, "%s: minibatch size above 65535 is not supported", fn);
+    B200DR_CHECK(B200DR_ALIGNED16(rast), "%s: rast input tensor not aligned to float4", fn);
+    B200DR_CHECK(B200DR_ALIGNED16(rast_db), "%s: rast_db input tensor not aligned to float4", fn);
+    B200DR_CHECK(diff_all || n_diff <= IP_MAX_DIFF, "%s: too many entries in diff_attrs list (increase IP_MAX_DIFF_ATTRS)", fn);
+    B200DR_CHECK(n_diff == 0 || rast_db, "%s: rast_db is required when diff_attrs is given", fn);
+    p.tri = tri; p.attr = attr; p.rast = rast; p.rast_db = rast_db;
+    p.N = N; p.H = H; p.W = W; p.V = V; p.T = T; p.A = A;
+    p.attr_bc = attr_bc; p.instance_mode = instance_mode; p.diff_all = diff_all;
+    p.D = diff_all ? A : n_diff;
+    if (!diff_all) for (int i = 0; i < n_diff; i++) p.diff[i] = diff_list[i];
+    p.chunks = (int)(((size_t)H * W + IP_THREADS - 1) / IP_THREADS);
+    return 0;
+}
+
+} // namespace
+
+extern "C" int b200dr_interpolate_fwd(const float* attr, const float* rast, const int32_t* tri, const float* rast_db,
+                                      int N, int H, int W, int V, int T, int A, int attr_bc, int instance_mode,
+                                      int diff_all, const int32_t* diff_list, int n_diff,
+                                      float* out, float* out_da, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    InterpParams p = {};
+    bool da = (diff_all || n_diff > 0);
+    if (fill_params(p, da ? "interpolate_fwd_da()" : "interpolate_fwd()", attr, rast, tri, da ? rast_db : 0, N, H, W, V, T, A, attr_bc, instance_mode,
+                    da ? diff_all : 0, diff_list, da ? n_diff : 0)) return 1;
+    if (!da) p.D = 0;
+    p.out = out; p.out_da = out_da;
+    size_t smem = (size_t)IP_THREADS * (A + 2 * p.D) * sizeof(float);
+    p.staged = smem <= 96 * 1024;
+    if (!p.staged) smem = 0;
+    int gx = p.chunks;
+    int cap = (b200dr_num_sms() * 16 + N - 1) / N;
+    if (gx > cap) gx = cap;
+    dim3 grid(gx, N);
+    if (da)
+    {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(interpolate_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        interpolate_fwd_kernel<true><<<grid, IP_THREADS, smem, stream>>>(p);
+    }
+    else
+    {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(interpolate_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        interpolate_fwd_kernel<false><<<grid, IP_THREADS, smem, stream>>>(p);
+    }
+    B200DR_CHECK_LAUNCH("interpolate_fwd()");
+    return 0;
+}
+
+extern "C" int b200dr_interpolate_grad(const float* attr, const float* rast, const int32_t* tri, const float* dy,
+                                       const float* rast_db, const float* dda,
+                                       int N, int H, int W, int V, int T, int A, int attr_bc, int instance_mode,
+                                       int diff_all, const int32_t* diff_list, int n_diff,
+                                       float* g_attr, float* g_rast, float* g_rast_db, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    InterpParams p = {};
+    bool da = (diff_all || n_diff > 0);
+    if (fill_params(p, da ? "interpolate_grad_da()" : "interpolate_grad()", attr, rast, tri, da ? rast_db : 0, N, H, W, V, T, A, attr_bc, instance_mode,
+                    da ? diff_all : 0, diff_list, da ? n_diff : 0)) return 1;
+    if (!da) p.D = 0;
+    B200DR_CHECK(B200DR_ALIGNED16(g_rast) && B200DR_ALIGNED16(g_rast_db), "interpolate_grad(): gradient output tensors not aligned to float4");
+    p.dy = dy; p.dda = dda; p.g_attr = g_attr; p.g_rast = g_rast; p.g_rast_db = g_rast_db;
+
+    size_t stage = (size_t)IP_THREADS * (A + 2 * p.D) * sizeof(float);
+    p.staged = stage <= 32 * 1024;
+    if (!p.staged) stage = 0;
+    size_t accb = (size_t)V * A * sizeof(float);
+    p.use_smem_acc = (accb + stage <= 96 * 1024) ? 1 : 0;
+    size_t smem = stage + (p.use_smem_acc ? accb : 0);
+
+    int gx;
+    if (p.use_smem_acc) gx = (b200dr_num_sms() * 4 + N - 1) / N;
+    else                gx = (b200dr_num_sms() * 16 + N - 1) / N;
+    if (gx > p.chunks) gx = p.chunks;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, N);
+    if (da)
+    {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(interpolate_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        interpolate_grad_kernel<true><<<grid, IP_THREADS, smem, stream>>>(p);
+    }
+    else
+    {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(interpolate_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        interpolate_grad_kernel<false><<<grid, IP_THREADS, smem, stream>>>(p);
+    }
+    B200DR_CHECK_LAUNCH("interpolate_grad()");
+    return 0;
+}

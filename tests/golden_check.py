@@ -1,0 +1,59 @@
+"""Compare the CPU oracle with one golden file produced by tests/golden/make_golden.py (reference outputs on a B200)."""
+import numpy as np
+
+import oracle
+from util import assert_close, assert_grad_close
+
+
+def _s(x):
+    return str(x) if not isinstance(x, str) else x
+
+
+def check_oracle_against_golden(g):
+    kind = _s(g["kind"])
+    if kind == "raster":
+        pos, tri, res = g["pos"], g["tri"], tuple(int(v) for v in g["res"])
+        o = oracle.rasterize_fwd(pos, tri, res)
+        ref_ids = g["rast"][..., 3].astype(np.int64)
+        assert np.array_equal(o["tri_id"], ref_ids), "%d id mismatches" % (o["tri_id"] != ref_ids).sum()
+        assert_close(o["rast"][..., :3], g["rast"][..., :3], 2e-5, 1e-4, "uvz", max_bad_frac=2e-3, hard_atol=5e-2)
+        assert_close(o["rast_db"], g["rast_db"], 1e-5, 1e-3, "rast_db", max_bad_frac=3e-3)
+        # gradients and downstream ops are evaluated on the REFERENCE's rast so that only the op under test differs
+        gp = oracle.rasterize_grad(pos, tri, g["rast"], g["dy"], g["ddb"])
+        assert_grad_close(gp, g["g_pos"], 5e-4, "rasterize g_pos")
+        out, out_da = oracle.interpolate_fwd(g["attr"], g["rast"], tri, g["rast_db"], "all")
+        assert_close(out, g["ip_out"], 1e-5, 1e-5, "interpolate out")
+        assert_close(out_da, g["ip_out_da"], 1e-5, 1e-4, "interpolate out_da")
+        ga, gr, gdb = oracle.interpolate_grad(g["attr"], g["rast"], tri, g["ip_dy"], g["rast_db"], g["ip_dda"], "all")
+        assert_grad_close(ga, g["ip_g_attr"], 5e-4, "interpolate g_attr")
+        assert_close(gr, g["ip_g_rast"], 1e-5, 1e-4, "interpolate g_rast")
+        assert_close(gdb, g["ip_g_rast_db"], 1e-5, 1e-4, "interpolate g_rast_db")
+        aa, items = oracle.antialias_fwd(g["color"], g["rast"], pos, tri)
+        assert_close(aa, g["aa_out"], 2e-6, 1e-5, "antialias out", max_bad_frac=1e-3, hard_atol=1e-2)
+        gc, gpa = oracle.antialias_grad(g["color"], g["rast"], pos, tri, g["aa_dy"], items)
+        assert_close(gc, g["aa_g_color"], 1e-5, 1e-4, "antialias g_color", max_bad_frac=1e-3)
+        assert_grad_close(gpa, g["aa_g_pos"], 2e-3, "antialias g_pos")
+        prev = None
+        for layer in range(g["peel_ids"].shape[0]):
+            o = oracle.rasterize_fwd(pos, tri, res, peel_depth=prev)
+            assert np.array_equal(o["tri_id"], g["peel_ids"][layer]), "peel layer %d" % layer
+            prev = o["depth"]
+    elif kind == "range":
+        o = oracle.rasterize_fwd(g["pos"], g["tri"], tuple(int(v) for v in g["res"]), ranges=g["ranges"])
+        assert np.array_equal(o["tri_id"], g["rast"][..., 3].astype(np.int64))
+    elif kind == "texture":
+        kw = dict(filter_mode=_s(g["filter_mode"]), boundary_mode=_s(g["boundary_mode"]))
+        uv_da = g["uv_da"] if "uv_da" in g else None
+        bias = g["bias"] if "bias" in g else None
+        out = oracle.texture_fwd(g["tex"], g["uv"], uv_da, bias, **kw)
+        assert_close(out, g["out"], 2e-5, 1e-4, "texture out", max_bad_frac=2e-3)
+        gr = oracle.texture_grad(g["tex"], g["uv"], g["dy"], uv_da, bias, **kw)
+        assert_grad_close(gr["g_tex"], g["g_tex"], 2e-3, "g_tex")
+        if "g_uv" in g:
+            assert_close(gr["g_uv"], g["g_uv"], 1e-3, 1e-3, "g_uv", max_bad_frac=5e-3)
+        if "g_uv_da" in g:
+            assert_close(gr["g_uv_da"], g["g_uv_da"], 1e-3, 2e-3, "g_uv_da", max_bad_frac=5e-3)
+        if "g_bias" in g:
+            assert_close(gr["g_bias"], g["g_bias"], 1e-4, 1e-3, "g_bias", max_bad_frac=5e-3)
+    else:
+        raise AssertionError("unknown golden kind " + kind)

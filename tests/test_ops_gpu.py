@@ -1,0 +1,341 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the torch front end) against the CPU oracle and, when
+oracle/_ref is present, against the unmodified reference CUDA extension running on the same GPU.
+
+Tolerances: triangle id / coverage exact; u, v, z/w, rast_db, interpolated attributes and colours
+abs <= 1e-6 + 1e-5*|x| against the reference build (same FMA contraction) and a looser bound against the
+uncontracted CPU oracle; gradients |g - g_ref|_inf <= 1e-4 * |g_ref|_inf.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import workloads as wl
+from util import assert_close, assert_grad_close, load_reference
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+@pytest.fixture(scope="module")
+def dr():
+    import nvdiffrast_b200.torch as dr
+    return dr
+
+
+@pytest.fixture(scope="module")
+def ctx(dr):
+    return dr.RasterizeCudaContext()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    r = load_reference()
+    if r is None:
+        pytest.skip("oracle/_ref (reference build) not available")
+    return r
+
+
+@pytest.fixture(scope="module")
+def ref_ctx(ref):
+    return ref.RasterizeCudaContext()
+
+
+SCENES = {
+    "triangle": lambda: (wl.triangle_scene()[0], wl.triangle_scene()[1], (256, 256)),
+    "cube": lambda: (wl.config_c2(n=3, res=128)["pos"], wl.config_c2()["tri"], (128, 128)),
+    "cube_odd": lambda: (wl.config_c2(n=2, res=64)["pos"], wl.config_c2()["tri"], (45, 77)),
+    "sphere": lambda: (wl.config_c3(n=2, res=256)["pos"], wl.config_c3(n=1, res=8)["tri"], (256, 256)),
+    "soup": lambda: wl.soup_scene(2, 300, 1) + ((96, 96),),
+    "soup_big": lambda: wl.soup_scene(1, 2000, 2, size=0.15) + ((200, 160),),
+    "grid": lambda: wl.grid_aligned_scene() + ((32, 32),),
+    "zfight": lambda: wl.zfight_scene() + ((64, 64),),
+}
+
+
+def run_rasterize(dr, ctx, pos, tri, res, path=0, ranges=None):
+    ctx.raster_path = path
+    try:
+        rast, db = dr.rasterize(ctx, cu(pos), cu(tri), res, ranges=ranges)
+    finally:
+        ctx.raster_path = 0
+    torch.cuda.synchronize()
+    return rast.cpu().numpy(), db.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+@pytest.mark.parametrize("path", [1, 2])
+def test_rasterize_vs_oracle(dr, ctx, name, path):
+    pos, tri, res = SCENES[name]()
+    o = oracle.rasterize_fwd(pos, tri, res)
+    rast, db = run_rasterize(dr, ctx, pos, tri, res, path)
+    ids = rast[..., 3].astype(np.int64)
+    assert np.array_equal(ids, o["tri_id"]), "%s path %d: %d pixels with a different triangle id" % (name, path, (ids != o["tri_id"]).sum())
+    assert_close(rast[..., :3], o["rast"][..., :3], 2e-5, 1e-4, name + " uvz", max_bad_frac=1e-3, hard_atol=5e-2)
+    assert_close(db, o["rast_db"], 1e-5, 1e-3, name + " db", max_bad_frac=2e-3)
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_rasterize_paths_identical(dr, ctx, name):
+    pos, tri, res = SCENES[name]()
+    a = run_rasterize(dr, ctx, pos, tri, res, 1)
+    b = run_rasterize(dr, ctx, pos, tri, res, 2)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_rasterize_range_mode(dr, ctx):
+    pos, tri, res = SCENES["soup"]()
+    pos2d = np.ascontiguousarray(pos[0])
+    ranges = torch.tensor([[0, 100], [100, 150], [37, 1], [250, 50]], dtype=torch.int32)
+    o = oracle.rasterize_fwd(pos2d, tri, res, ranges=ranges.numpy())
+    for path in (1, 2):
+        rast, db = run_rasterize(dr, ctx, pos2d, tri, res, path, ranges=ranges)
+        assert np.array_equal(rast[..., 3].astype(np.int64), o["tri_id"])
+
+
+def test_depth_peeler(dr, ctx):
+    pos, tri, res = SCENES["soup"]()
+    for path in (1, 2):
+        ctx.raster_path = path
+        try:
+            with dr.DepthPeeler(ctx, cu(pos), cu(tri), res) as peeler:
+                prev = None
+                for layer in range(3):
+                    rast, _ = peeler.rasterize_next_layer()
+                    o = oracle.rasterize_fwd(pos, tri, res, peel_depth=prev)
+                    assert np.array_equal(rast[..., 3].cpu().numpy().astype(np.int64), o["tri_id"]), "layer %d path %d" % (layer, path)
+                    prev = o["depth"]
+        finally:
+            ctx.raster_path = 0
+
+
+def _rand_like(shape, seed):
+    return np.random.default_rng(seed).normal(size=shape).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", ["cube", "sphere", "soup"])
+@pytest.mark.parametrize("with_db", [False, True])
+def test_rasterize_grad_vs_oracle(dr, ctx, name, with_db):
+    pos, tri, res = SCENES[name]()
+    tpos = cu(pos).requires_grad_(True)
+    rast, db = dr.rasterize(ctx, tpos, cu(tri), res, grad_db=with_db)
+    dy = _rand_like(rast.shape, 5); ddb = _rand_like(rast.shape, 6)
+    loss = (rast * cu(dy)).sum() + ((db * cu(ddb)).sum() if with_db else 0.0)
+    loss.backward()
+    g = tpos.grad.cpu().numpy()
+    go = oracle.rasterize_grad(pos, tri, rast.detach().cpu().numpy(), dy, ddb if with_db else None)
+    assert_grad_close(g, go, 2e-4, name + " g_pos")
+
+
+@pytest.mark.parametrize("name", ["cube", "sphere", "soup"])
+@pytest.mark.parametrize("A", [1, 3, 4, 7])
+def test_interpolate_vs_oracle(dr, ctx, name, A):
+    pos, tri, res = SCENES[name]()
+    V = pos.shape[1]
+    rast, db = dr.rasterize(ctx, cu(pos), cu(tri), res)
+    rast_np, db_np = rast.cpu().numpy(), db.cpu().numpy()
+    for mode in ("shared", "instanced", "broadcast"):
+        attr = _rand_like((V, A) if mode == "shared" else ((pos.shape[0], V, A) if mode == "instanced" else (1, V, A)), 7)
+        if mode == "shared":
+            continue    # range-mode attr [V,A] only pairs with range-mode raster; covered in test_interpolate_range_mode
+        tattr = cu(attr).requires_grad_(True)
+        trast = rast.detach().clone().requires_grad_(True)
+        out, _ = dr.interpolate(tattr, trast, cu(tri))
+        oo, _ = oracle.interpolate_fwd(attr, rast_np, tri)
+        assert_close(out.detach().cpu().numpy(), oo, 1e-6 * max(1.0, np.abs(attr).max()), 1e-5, "%s A=%d %s out" % (name, A, mode))
+        dy = _rand_like(out.shape, 8)
+        (out * cu(dy)).sum().backward()
+        ga, gr, _ = oracle.interpolate_grad(attr, rast_np, tri, dy)
+        assert_grad_close(tattr.grad.cpu().numpy(), ga, 2e-4, "g_attr")
+        assert_close(trast.grad.cpu().numpy(), gr, 1e-5, 1e-4, "g_rast")
+
+
+@pytest.mark.parametrize("diff", ["all", [0, 2], [-1], [1, 1, 0]])
+def test_interpolate_da_vs_oracle(dr, ctx, diff):
+    pos, tri, res = SCENES["sphere"]()
+    V, A = pos.shape[1], 3
+    rast, db = dr.rasterize(ctx, cu(pos), cu(tri), res)
+    rast_np, db_np = rast.cpu().numpy(), db.cpu().numpy()
+    attr = _rand_like((pos.shape[0], V, A), 9)
+    tattr = cu(attr).requires_grad_(True)
+    trast = rast.detach().clone().requires_grad_(True)
+    tdb = db.detach().clone().requires_grad_(True)
+    out, out_da = dr.interpolate(tattr, trast, cu(tri), rast_db=tdb, diff_attrs=diff)
+    oo, oda = oracle.interpolate_fwd(attr, rast_np, tri, db_np, diff)
+    assert out_da.shape == oda.shape
+    assert_close(out.detach().cpu().numpy(), oo, 1e-5, 1e-5, "out")
+    assert_close(out_da.detach().cpu().numpy(), oda, 1e-5, 1e-4, "out_da")
+    dy = _rand_like(out.shape, 10); dda = _rand_like(out_da.shape, 11)
+    ((out * cu(dy)).sum() + (out_da * cu(dda)).sum()).backward()
+    ga, gr, gdb = oracle.interpolate_grad(attr, rast_np, tri, dy, db_np, dda, diff)
+    assert_grad_close(tattr.grad.cpu().numpy(), ga, 2e-4, "g_attr")
+    assert_close(trast.grad.cpu().numpy(), gr, 1e-5, 1e-4, "g_rast")
+    assert_close(tdb.grad.cpu().numpy(), gdb, 1e-5, 1e-4, "g_rast_db")
+
+
+def test_interpolate_range_mode(dr, ctx):
+    pos, tri, res = SCENES["soup"]()
+    pos2d = np.ascontiguousarray(pos[0])
+    ranges = torch.tensor([[0, 150], [150, 150]], dtype=torch.int32)
+    rast, _ = dr.rasterize(ctx, cu(pos2d), cu(tri), res, ranges=ranges)
+    attr = _rand_like((pos2d.shape[0], 5), 12)
+    tattr = cu(attr).requires_grad_(True)
+    out, _ = dr.interpolate(tattr, rast, cu(tri))
+    oo, _ = oracle.interpolate_fwd(attr, rast.cpu().numpy(), tri)
+    assert_close(out.detach().cpu().numpy(), oo, 1e-5, 1e-5, "out")
+    dy = _rand_like(out.shape, 13)
+    (out * cu(dy)).sum().backward()
+    ga, _, _ = oracle.interpolate_grad(attr, rast.cpu().numpy(), tri, dy)
+    assert_grad_close(tattr.grad.cpu().numpy(), ga, 2e-4, "g_attr")
+
+
+@pytest.mark.parametrize("name", ["cube", "sphere", "triangle"])
+@pytest.mark.parametrize("C", [1, 3, 4])
+def test_antialias_vs_oracle(dr, ctx, name, C):
+    pos, tri, res = SCENES[name]()
+    rast, _ = dr.rasterize(ctx, cu(pos), cu(tri), res)
+    rast_np = rast.cpu().numpy()
+    color = np.random.default_rng(14).uniform(size=rast_np.shape[:3] + (C,)).astype(np.float32)
+    tcol = cu(color).requires_grad_(True)
+    tpos = cu(pos).requires_grad_(True)
+    out = dr.antialias(tcol, rast, tpos, cu(tri))
+    oo, items = oracle.antialias_fwd(color, rast_np, pos, tri)
+    assert_close(out.detach().cpu().numpy(), oo, 2e-6, 1e-5, name + " aa out", max_bad_frac=1e-4, hard_atol=1e-3)
+    dy = _rand_like(out.shape, 15)
+    (out * cu(dy)).sum().backward()
+    gc, gp = oracle.antialias_grad(color, rast_np, pos, tri, dy, items)
+    assert_close(tcol.grad.cpu().numpy(), gc, 1e-5, 1e-4, "g_color", max_bad_frac=1e-4)
+    assert_grad_close(tpos.grad.cpu().numpy(), gp, 5e-4, "aa g_pos")
+    # precomputed topology gives the same result
+    topo = dr.antialias_construct_topology_hash(cu(tri))
+    out2 = dr.antialias(cu(color), rast, cu(pos), cu(tri), topology_hash=topo)
+    assert_close(out2.cpu().numpy(), out.detach().cpu().numpy(), 1e-6, 1e-6, "topology reuse")
+
+
+TEX_CASES = [
+    ("nearest", "wrap", False, False), ("linear", "wrap", False, False), ("linear", "clamp", False, False), ("linear", "zero", False, False),
+    ("linear-mipmap-nearest", "wrap", True, False), ("linear-mipmap-linear", "wrap", True, False),
+    ("linear-mipmap-linear", "clamp", True, True), ("linear-mipmap-linear", "zero", False, True), ("linear-mipmap-nearest", "clamp", False, True),
+]
+
+
+@pytest.mark.parametrize("filter_mode,boundary_mode,use_da,use_bias", TEX_CASES)
+@pytest.mark.parametrize("C", [1, 3, 4])
+def test_texture_vs_oracle(dr, filter_mode, boundary_mode, use_da, use_bias, C):
+    rng = np.random.default_rng(16)
+    N, H, W = 2, 40, 56
+    tex = rng.uniform(size=(1 if C != 3 else 2, 32, 64, C)).astype(np.float32)
+    uv = rng.uniform(-0.3, 1.3, size=(N, H, W, 2)).astype(np.float32)
+    uv_da = (rng.normal(size=(N, H, W, 4)) * 0.03).astype(np.float32) if use_da else None
+    bias = rng.uniform(-1, 3, size=(N, H, W)).astype(np.float32) if use_bias else None
+    ttex = cu(tex).requires_grad_(True); tuv = cu(uv).requires_grad_(True)
+    tda = cu(uv_da).requires_grad_(True) if use_da else None
+    tbias = cu(bias).requires_grad_(True) if use_bias else None
+    out = dr.texture(ttex, tuv, tda, tbias, filter_mode=filter_mode, boundary_mode=boundary_mode)
+    oo = oracle.texture_fwd(tex, uv, uv_da, bias, filter_mode=filter_mode, boundary_mode=boundary_mode)
+    # __log2f is approximate: a pixel whose level sits on an integer boundary may pick the neighbouring level pair
+    assert_close(out.detach().cpu().numpy(), oo, 2e-5, 1e-4, "tex out", max_bad_frac=2e-3)
+    dy = _rand_like(out.shape, 17)
+    (out * cu(dy)).sum().backward()
+    g = oracle.texture_grad(tex, uv, dy, uv_da, bias, filter_mode=filter_mode, boundary_mode=boundary_mode)
+    assert_grad_close(ttex.grad.cpu().numpy(), g["g_tex"], 2e-3, "g_tex")
+    if filter_mode != "nearest":
+        assert_close(tuv.grad.cpu().numpy(), g["g_uv"], 1e-3, 1e-3, "g_uv", max_bad_frac=5e-3)
+    if filter_mode == "linear-mipmap-linear":
+        if use_da:
+            assert_close(tda.grad.cpu().numpy(), g["g_uv_da"], 1e-3, 2e-3, "g_uv_da", max_bad_frac=5e-3)
+        if use_bias:
+            assert_close(tbias.grad.cpu().numpy(), g["g_bias"], 1e-4, 1e-3, "g_bias", max_bad_frac=5e-3)
+
+
+def test_texture_mip_stack_and_wrapper(dr):
+    rng = np.random.default_rng(18)
+    tex = rng.uniform(size=(1, 16, 32, 3)).astype(np.float32)
+    uv = rng.uniform(size=(1, 24, 24, 2)).astype(np.float32)
+    bias = rng.uniform(0, 3, size=(1, 24, 24)).astype(np.float32)
+    mip = dr.texture_construct_mip(cu(tex), max_mip_level=3)
+    om = oracle.texture_construct_mip(tex, 3)
+    assert_close(mip.mip.cpu().numpy(), om["mip"][:om["total"]], 1e-6, 1e-6, "mip stack")
+    a = dr.texture(cu(tex), cu(uv), mip_level_bias=cu(bias), mip=mip, filter_mode="linear-mipmap-linear")
+    b = dr.texture(cu(tex), cu(uv), mip_level_bias=cu(bias), max_mip_level=3, filter_mode="linear-mipmap-linear")
+    assert torch.equal(a, b)
+    # custom stack = the same levels as separate tensors; gradients land on the levels
+    levels = []
+    off = om["offsets"]
+    for L in range(1, 4):
+        w, h = max(32 >> L, 1), max(16 >> L, 1)
+        levels.append(cu(om["mip"][off[L]:off[L] + h * w * 3].reshape(1, h, w, 3)).requires_grad_(True))
+    c = dr.texture(cu(tex), cu(uv), mip_level_bias=cu(bias), mip=levels, filter_mode="linear-mipmap-linear")
+    assert_close(c.detach().cpu().numpy(), a.cpu().numpy(), 1e-6, 1e-6, "custom stack")
+    c.sum().backward()
+    assert all(l.grad is not None and float(l.grad.abs().sum()) > 0 for l in levels)
+
+
+def test_error_behaviour(dr, ctx):
+    pos, tri, res = SCENES["triangle"]()
+    with pytest.raises(RuntimeError):
+        dr.rasterize(ctx, torch.from_numpy(pos), cu(tri), res)          # CPU tensor: no CPU path
+    with pytest.raises(RuntimeError):
+        dr.rasterize(ctx, cu(pos).double(), cu(tri), res)
+    with pytest.raises(RuntimeError):
+        dr.interpolate(cu(pos)[..., :3].transpose(1, 2), cu(np.zeros((1, 4, 4, 4), np.float32)), cu(tri))
+    with dr.DepthPeeler(ctx, cu(pos), cu(tri), res):
+        r = dr.rasterize(ctx, cu(pos), cu(tri), res)
+        assert isinstance(r, RuntimeError)                                # reference returns (not raises) this error
+
+
+# ----------------------------------------------------------------------------------------------
+# Against the unmodified reference running on the same GPU
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_rasterize_vs_reference(dr, ctx, ref, ref_ctx, name):
+    pos, tri, res = SCENES[name]()
+    r_rast, r_db = ref.rasterize(ref_ctx, cu(pos), cu(tri), res)
+    for path in (1, 2):
+        rast, db = run_rasterize(dr, ctx, pos, tri, res, path)
+        rr = r_rast.cpu().numpy()
+        assert np.array_equal(rast[..., 3], rr[..., 3]), "%s path %d: %d id mismatches vs reference" % (name, path, (rast[..., 3] != rr[..., 3]).sum())
+        assert_close(rast[..., :3], rr[..., :3], 1e-6, 1e-5, name + " uvz vs ref", max_bad_frac=1e-4, hard_atol=1e-2)
+        assert_close(db, r_db.cpu().numpy(), 1e-6, 1e-4, name + " db vs ref", max_bad_frac=1e-3)
+
+
+def _full_chain(mod, rctx, c, n, with_tex=True):
+    pos = cu(c["pos"][:n]).requires_grad_(True)
+    tri = cu(c["tri"])
+    rast, db = mod.rasterize(rctx, pos, tri, c["res"])
+    if with_tex:
+        uv = cu(c["uv"]).requires_grad_(True); tex = cu(c["tex"]).requires_grad_(True)
+        texc, texd = mod.interpolate(uv[None, ...], rast, cu(c["uv_idx"]), rast_db=db, diff_attrs="all")
+        color = mod.texture(tex, texc, texd, filter_mode="linear-mipmap-linear", max_mip_level=8)
+        leaves = dict(pos=pos, uv=uv, tex=tex)
+    else:
+        attr = cu(c["attr"]).requires_grad_(True)
+        color, _ = mod.interpolate(attr[None, ...], rast, tri)
+        leaves = dict(pos=pos, attr=attr)
+    out = mod.antialias(color, rast, pos, tri)
+    return rast, color, out, leaves
+
+
+@pytest.mark.parametrize("cfg", ["c2", "c3"])
+def test_chain_vs_reference(dr, ctx, ref, ref_ctx, cfg):
+    if cfg == "c2":
+        c, n, with_tex = wl.config_c2(n=4, res=512), 4, False
+    else:
+        c, n, with_tex = wl.config_c3(n=2, res=1024, tex_res=256), 2, True
+    a_rast, a_color, a_out, a_leaves = _full_chain(dr, ctx, c, n, with_tex)
+    b_rast, b_color, b_out, b_leaves = _full_chain(ref, ref_ctx, c, n, with_tex)
+    assert torch.equal(a_rast[..., 3], b_rast[..., 3])
+    assert_close(a_color.detach().cpu().numpy(), b_color.detach().cpu().numpy(), 2e-5, 1e-4, "color", max_bad_frac=2e-3)
+    assert_close(a_out.detach().cpu().numpy(), b_out.detach().cpu().numpy(), 2e-5, 1e-4, "aa out", max_bad_frac=2e-3)
+    dy = cu(_rand_like(tuple(a_out.shape), 19))
+    (a_out * dy).sum().backward()
+    (b_out * dy).sum().backward()
+    for k in a_leaves:
+        assert_grad_close(a_leaves[k].grad.cpu().numpy(), b_leaves[k].grad.cpu().numpy(), 2e-3, cfg + " grad " + k)

@@ -1,0 +1,45 @@
+"""Helpers shared by the parity tests."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def load_reference():
+    """Import the unmodified reference (built into oracle/_ref by oracle/build_ref.sh); None if absent/unloadable."""
+    if not os.path.isdir(os.path.join(REF_DIR, "nvdiffrast")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        import nvdiffrast.torch as ref_dr
+        return ref_dr
+    except Exception as e:  # e.g. ABI mismatch on another image
+        print("reference not loadable:", e)
+        return None
+
+
+def close_stats(a, b, atol, rtol):
+    """-> (max abs err, fraction of elements violating |a-b| <= atol + rtol*|b|)."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    err = np.abs(a - b)
+    bad = err > (atol + rtol * np.abs(b))
+    return (float(err.max()) if err.size else 0.0), (float(bad.mean()) if err.size else 0.0)
+
+
+def assert_close(a, b, atol, rtol, name="", max_bad_frac=0.0, hard_atol=None):
+    mx, frac = close_stats(a, b, atol, rtol)
+    assert frac <= max_bad_frac, "%s: %.3g of elements outside atol=%g rtol=%g (max abs err %.3g)" % (name, frac, atol, rtol, mx)
+    if hard_atol is not None:
+        assert mx <= hard_atol, "%s: max abs err %.3g > %g" % (name, mx, hard_atol)
+
+
+def assert_grad_close(g, g_ref, rel=1e-4, name=""):
+    """|g - g_ref|_inf <= rel * |g_ref|_inf  (atomic summation order differs between implementations)."""
+    g = np.asarray(g, np.float64); g_ref = np.asarray(g_ref, np.float64)
+    scale = max(float(np.abs(g_ref).max()), 1e-30)
+    err = float(np.abs(g - g_ref).max())
+    assert err <= rel * scale, "%s: max err %.3g vs scale %.3g (rel %.3g > %g)" % (name, err, scale, err / scale, rel)
