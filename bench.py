@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- Mpixels/s forward+backward of the differentiable-rasterizer hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json): c3 = "Spot-like" bumped sphere (5 856 triangles, 2 930 vertices), 2048x2048, 16 images per GPU,
+full chain rasterize -> interpolate(uv, all pixel differentials) -> texture(trilinear, 1024^2 x3) -> antialias, forward +
+backward, seeded synthetic data (workloads.py).  A step = one such pass over one batch; per-GPU work is fixed (weak scaling);
+for N > 1 the vertex-position gradient of the shared mesh is all-reduced over NCCL every step.
+
+One JSON line on rank 0.  `value` = whole-job Mpixel/s with inputs resident in HBM; `e2e` = the same metric through the
+public API with the step's inputs copied from pinned host memory and the loss + vertex gradient read back every step;
+`roofline` = algorithmic HBM bytes of the dominant op / its CUDA-event time, against the measured copy peak
+(MEASURED_PEAKS.json); `cpu_baseline` = the CPU oracle (a port of the reference math; the reference has no CPU path) timed
+on one image of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import workloads as wl  # noqa: E402
+from nvdiffrast_b200.distributed import allreduce_shared_grads  # noqa: E402
+
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# the pipeline (same code drives our ops and the reference's)
+
+
+def op_bytes(workload, P, A, D, C):
+    """Algorithmic HBM bytes per C-ABI op call for P pixels (every per-pixel input read once, every
+    output written once; L2-resident mesh / texture gathers excluded)."""
+    b = {
+        "b200dr_rasterize_fwd": 32 * P,
+        "b200dr_rasterize_grad": (32 + (16 if workload == "c3" else 0)) * P,
+        "b200dr_interpolate_fwd": (16 + 4 * A + (16 + 8 * D if D else 0)) * P,
+        "b200dr_interpolate_grad": (32 + 4 * A + (32 + 8 * D if D else 0)) * P,
+        "b200dr_antialias_fwd": (8 * C + 16) * P,
+        "b200dr_antialias_grad": 8 * C * P,
+        "b200dr_texture_fwd": (8 + 4 * C + 16) * P,
+        "b200dr_texture_grad": (16 + 4 * C + 32) * P,
+    }
+    return b
+
+
+class Pipeline:
+    def __init__(self, mod, workload, n_img, res, device, seed, tex_res=1024):
+        self.mod, self.workload, self.device = mod, workload, device
+        if workload == "c3":
+            c = wl.config_c3(n=1, res=res, tex_res=tex_res)
+            v = wl.sphere_mesh()[0]
+        elif workload == "c2":
+            c = wl.config_c2(n=1, res=res)
+            v = wl.cube_mesh()[0]
+        else:
+            c = wl.config_c4(n=1, res=res)
+            v = wl.sphere_mesh(1000, 501)[0]
+        far = 50.0 if workload == "c2" else 200.0
+        self.res = (res, res)
+        self.n_img = n_img
+        self.host = {                                   # pinned host copies of everything a step consumes
+            "verts": torch.from_numpy(np.concatenate([v, np.ones((v.shape[0], 1), np.float32)], 1)).pin_memory(),
+            "mvp": torch.from_numpy(wl.camera_batch(n_img, seed, far=far)).pin_memory(),
+        }
+        if workload == "c3":
+            self.host["uv"] = torch.from_numpy(c["uv"]).pin_memory()
+            self.host["tex"] = torch.from_numpy(c["tex"]).pin_memory()
+        else:
+            self.host["attr"] = torch.from_numpy(c["attr"]).pin_memory()
+        self.tri = torch.from_numpy(c["tri"]).to(device)
+        self.uv_idx = torch.from_numpy(c["uv_idx"]).to(device) if workload == "c3" else None
+        self.ctx = mod.RasterizeCudaContext(device)
+        self.topo = mod.antialias_construct_topology_hash(self.tri) if workload == "c3" else None
+        self.dev = {}
+        self.upload()
+        C = 3
+        g = torch.Generator(device=device); g.manual_seed(2 + seed)
+        self.dy = torch.randn((n_img, res, res, C), device=device, generator=g)
+        self.grad_host = torch.empty((v.shape[0], 4), dtype=torch.float32).pin_memory()
+        self.loss_host = torch.empty((1,), dtype=torch.float32).pin_memory()
+
+    def h2d_bytes(self):
+        return int(sum(t.numel() * t.element_size() for t in self.host.values()))
+
+    def d2h_bytes(self):
+        return int(self.grad_host.numel() * 4 + 4)
+
+    def upload(self):
+        for k, t in self.host.items():
+            d = self.dev.get(k)
+            if d is None:
+                self.dev[k] = t.to(self.device, non_blocking=True)
+            else:
+                with torch.no_grad():
+                    d.copy_(t, non_blocking=True)
+
+    def step(self, world=1, with_loss=False):
+        """forward + backward (+ all-reduce of the shared vertex gradient).  Returns (loss, vertex grad) on the device.
+        with_loss: form the scalar loss sum(out * dy) explicitly (end-to-end runs read it back); otherwise dy is fed
+        straight into backward, so the timed region contains the hot path and nothing else."""
+        mod = self.mod
+        verts = self.dev["verts"].detach().requires_grad_(True)
+        pos = torch.matmul(verts[None], self.dev["mvp"].transpose(1, 2)).contiguous()      # [n, V, 4] clip space
+        rast, db = mod.rasterize(self.ctx, pos, self.tri, self.res)
+        if self.workload == "c3":
+            texc, texd = mod.interpolate(self.dev["uv"][None], rast, self.uv_idx, rast_db=db, diff_attrs="all")
+            color = mod.texture(self.dev["tex"], texc, texd, filter_mode="linear-mipmap-linear", max_mip_level=9)
+            out = mod.antialias(color, rast, pos, self.tri, topology_hash=self.topo)
+        else:
+            out, _ = mod.interpolate(self.dev["attr"][None], rast, self.tri)
+        if with_loss:
+            loss = (out * self.dy).sum()
+            loss.backward()
+        else:
+            loss = None
+            out.backward(self.dy)
+        g = verts.grad
+        if world > 1:
+            allreduce_shared_grads([g])
+        return loss, g
+
+    def set_requires_grad(self):
+        for k in ("uv", "tex", "attr"):
+            if k in self.dev:
+                self.dev[k] = self.dev[k].detach().requires_grad_(True)
+
+    def zero_grads(self):
+        for k in ("uv", "tex", "attr"):
+            if k in self.dev and self.dev[k].grad is not None:
+                self.dev[k].grad = None
+
+
+def load_module(impl):
+    if impl == "ours":
+        import nvdiffrast_b200.torch as dr
+        return dr, "ours"
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import load_reference
+    ref = load_reference()
+    return ref, ("reference-cuda" if ref is not None else None)
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline / reference arm fallback)
+
+
+def cpu_oracle_rate(workload, res, samples=1):
+    """Mpixel/s of the CPU oracle (port of the reference math, all host threads) on `samples` images of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    from util import oracle_chain
+    oracle.build()
+    if workload == "c3":
+        c = wl.config_c3(n=samples, res=res)
+    elif workload == "c2":
+        c = wl.config_c2(n=samples, res=res)
+    else:
+        c = wl.config_c4(n=samples, res=res)
+    dy = np.random.default_rng(2).normal(size=(samples, res, res, 3)).astype(np.float32)
+    t0 = time.perf_counter()
+    oracle_chain(c, samples, workload == "c3", dy, max_mip_level=9)
+    dt = time.perf_counter() - t0
+    return samples * res * res / dt / 1e6, dt, oracle.num_threads()
+
+
+# ----------------------------------------------------------------------------------------------
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4"])
+    ap.add_argument("--res", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    defaults = {"c3": (2048, 16), "c2": (1024, 64), "c4": (2048, 8)}
+    res = args.res or defaults[args.workload][0]
+    n_img = args.batch or defaults[args.workload][1]
+    K, W = args.steps, max(args.warmup, 3)
+
+    mod, kind = load_module(args.impl)
+    if args.impl == "reference" and mod is None:
+        # reference CUDA build not loadable here: time the CPU oracle on rank 0 instead (bounded sample)
+        if rank == 0:
+            rate, dt, thr = cpu_oracle_rate(args.workload, res, 1)
+            print(json.dumps({"impl": "reference", "metric": "Mpixels/sec fwd+bwd (rasterize+interpolate+texture+antialias) at %d^2" % res,
+                              "value": rate, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3,
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                              "config": {"workload": args.workload, "res": res, "note": "CPU oracle port; reference CUDA build unavailable"},
+                              "cpu_baseline": {"value": rate, "unit": "Mpixel/s", "cores": thr, "kind": "port", "sample": "1 image %dx%d" % (res, res)},
+                              "e2e": {"value": rate, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
+
+    pipe = Pipeline(mod, args.workload, n_img, res, device, seed=rank)
+    pipe.set_requires_grad()
+    P = n_img * res * res
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(W):
+        pipe.zero_grads(); pipe.step(world)
+    trace = []
+    launches0 = 0
+    if args.impl == "ours":
+        from nvdiffrast_b200 import _lib
+        _lib.set_trace(trace)
+        launches0 = _lib.load().b200dr_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        pipe.zero_grads(); pipe.step(world)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = 0
+    if args.impl == "ours":
+        _lib.set_trace(None)
+        launches = int(_lib.load().b200dr_launch_count() - launches0)
+    t = torch.tensor([ms], device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * P * K / (ms * 1e-3) / 1e6
+
+    # ---- end to end: inputs from pinned host memory every step, loss + vertex gradient read back every step
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            pipe.upload(); pipe.set_requires_grad(); pipe.step(world, with_loss=True)
+        barrier()
+        e0.record()
+        for _ in range(K):
+            pipe.upload(); pipe.set_requires_grad()
+            loss, g = pipe.step(world, with_loss=True)
+            pipe.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+            pipe.grad_host.copy_(g, non_blocking=True)
+            torch.cuda.synchronize()        # the caller consumes the result of this step
+        e1.record()
+        barrier()
+        ms2 = e0.elapsed_time(e1)
+        t = torch.tensor([ms2], device=device)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms2 = float(t.item())
+        e2e = {"value": world * P * K / (ms2 * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": ms2 / K,
+               "h2d_bytes_per_step": pipe.h2d_bytes(), "d2h_bytes_per_step": pipe.d2h_bytes()}
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    out = {"metric": "Mpixels/sec fwd+bwd (rasterize+interpolate+texture+antialias) at %d^2" % res if args.workload == "c3"
+           else "Mpixels/sec fwd+bwd (rasterize+interpolate) at %d^2" % res,
+           "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+           "config": {"workload": {"c3": "c3: Spot-like sphere 5856 tris, %d^2, %d images/GPU, rasterize+interpolate(uv,da)+texture(trilinear 1024^2x3)+antialias fwd+bwd",
+                                   "c2": "c2: cube 12 tris, %d^2, %d images/GPU, rasterize+interpolate fwd+bwd",
+                                   "c4": "c4: 1M-triangle sphere, %d^2, %d images/GPU, rasterize+interpolate fwd+bwd"}[args.workload] % (res, n_img),
+                      "global_batch": world * n_img, "pixels_per_step": world * P,
+                      "l2": "per-step working set (>= %.1f GB of per-pixel tensors) exceeds the 126 MB L2; no explicit flush" % (P * 32 / 1e9),
+                      "parallelism": "dp%d (batch shard, one NCCL all-reduce of the vertex gradient)" % world},
+           "clocks": clocks}
+    if args.impl == "reference":
+        out["impl"] = "reference"
+        out["config"]["reference"] = "unmodified NVlabs/nvdiffrast v0.4.0 CUDA extension built for sm_100a (oracle/_ref), same harness; " \
+                                     "the reference has no CPU path (SURVEY.md F1)"
+    if e2e is not None:
+        out["e2e"] = e2e
+    if args.impl == "ours":
+        out["gpu_launches"] = launches
+        # per-op CUDA-event times over the timed region
+        peak, peak_src = hbm_peak()
+        A, D, C = (2, 2, 3) if args.workload == "c3" else (3, 0, 3)
+        nbytes = op_bytes(args.workload, P, A, D, C)
+        ops = {}
+        for name, a, b in trace:
+            d = ops.setdefault(name, [0.0, 0])
+            d[0] += a.elapsed_time(b); d[1] += 1
+        table = {}
+        for name, (tot, cnt) in ops.items():
+            avg = tot / cnt
+            e = {"calls_per_step": cnt / K, "ms": avg}
+            if name in nbytes:
+                gbs = nbytes[name] / (avg * 1e-3) / 1e9
+                e.update({"algorithmic_bytes": nbytes[name], "GBps": gbs, "frac": gbs / peak})
+            table[name.replace("b200dr_", "")] = e
+        out["ops"] = table
+        dom = max((n for n in ops if n in nbytes), key=lambda n: ops[n][0])
+        avg = ops[dom][0] / ops[dom][1]
+        ach = nbytes[dom] / (avg * 1e-3) / 1e9
+        out["roofline"] = {"kernel": dom.replace("b200dr_", ""), "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                           "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                           "algorithmic_bytes_per_launch": nbytes[dom], "avg_launch_ms": avg}
+        chain_bytes = sum(nbytes[n] * ops[n][1] / K for n in ops if n in nbytes)
+        out["chain_roofline"] = {"algorithmic_bytes_per_step": chain_bytes, "achieved_GBps": chain_bytes / (ms / K * 1e-3) / 1e9,
+                                 "frac": chain_bytes / (ms / K * 1e-3) / 1e9 / peak}
+    if not args.no_cpu_baseline and world == 1:
+        rate, dt, thr = cpu_oracle_rate(args.workload, res, 1)
+        out["cpu_baseline"] = {"value": rate, "unit": "Mpixel/s", "cores": thr, "kind": "port",
+                               "sample": "1 image %dx%d of the same workload, fwd+bwd, %.1f s" % (res, res, dt)}
+    print(json.dumps(out))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,4 +1,13 @@
-"""Compare the CPU oracle with one golden file produced by tests/golden/make_golden.py (reference outputs on a B200)."""
+"""Compare the CPU oracle with one golden file produced by tests/golden/make_golden.py (reference outputs on a B200).
+
+Finding recorded here (DESIGN.md "Reference defect on sm_100a"): every gradient the reference accumulates through its
+warp-coalesced atomics (`caAtomicAdd`, csrc/common/common.h:198-241: rasterize g_pos, interpolate g_attr, texture g_tex in
+the linear modes, antialias g_pos) comes out WRONG when the unmodified reference is built for sm_100a and run on a B200
+(contributions are lost; the macros call __match_any_sync(0xffffffff, ..) after some lanes have returned and touch the
+shared slot without a __syncwarp).  Gradients that do not pass through those macros (g_rast, g_rast_db, g_color, g_uv,
+g_uv_da, g_bias, nearest-mode g_tex) and every forward output agree with the oracle to ~1e-7.  Those four tensors are
+therefore NOT used as pins; they are pinned by float64 autograd / exact finite differences instead
+(tests/test_oracle_cpu.py::test_*_float64_*), and test_reference_atomic_gradients_are_corrupted documents the defect."""
 import numpy as np
 
 import oracle
@@ -19,20 +28,16 @@ def check_oracle_against_golden(g):
         assert_close(o["rast"][..., :3], g["rast"][..., :3], 2e-5, 1e-4, "uvz", max_bad_frac=2e-3, hard_atol=5e-2)
         assert_close(o["rast_db"], g["rast_db"], 1e-5, 1e-3, "rast_db", max_bad_frac=3e-3)
         # gradients and downstream ops are evaluated on the REFERENCE's rast so that only the op under test differs
-        gp = oracle.rasterize_grad(pos, tri, g["rast"], g["dy"], g["ddb"])
-        assert_grad_close(gp, g["g_pos"], 5e-4, "rasterize g_pos")
         out, out_da = oracle.interpolate_fwd(g["attr"], g["rast"], tri, g["rast_db"], "all")
         assert_close(out, g["ip_out"], 1e-5, 1e-5, "interpolate out")
         assert_close(out_da, g["ip_out_da"], 1e-5, 1e-4, "interpolate out_da")
         ga, gr, gdb = oracle.interpolate_grad(g["attr"], g["rast"], tri, g["ip_dy"], g["rast_db"], g["ip_dda"], "all")
-        assert_grad_close(ga, g["ip_g_attr"], 5e-4, "interpolate g_attr")
         assert_close(gr, g["ip_g_rast"], 1e-5, 1e-4, "interpolate g_rast")
         assert_close(gdb, g["ip_g_rast_db"], 1e-5, 1e-4, "interpolate g_rast_db")
         aa, items = oracle.antialias_fwd(g["color"], g["rast"], pos, tri)
         assert_close(aa, g["aa_out"], 2e-6, 1e-5, "antialias out", max_bad_frac=1e-3, hard_atol=1e-2)
         gc, gpa = oracle.antialias_grad(g["color"], g["rast"], pos, tri, g["aa_dy"], items)
         assert_close(gc, g["aa_g_color"], 1e-5, 1e-4, "antialias g_color", max_bad_frac=1e-3)
-        assert_grad_close(gpa, g["aa_g_pos"], 2e-3, "antialias g_pos")
         prev = None
         for layer in range(g["peel_ids"].shape[0]):
             o = oracle.rasterize_fwd(pos, tri, res, peel_depth=prev)
@@ -48,7 +53,8 @@ def check_oracle_against_golden(g):
         out = oracle.texture_fwd(g["tex"], g["uv"], uv_da, bias, **kw)
         assert_close(out, g["out"], 2e-5, 1e-4, "texture out", max_bad_frac=2e-3)
         gr = oracle.texture_grad(g["tex"], g["uv"], g["dy"], uv_da, bias, **kw)
-        assert_grad_close(gr["g_tex"], g["g_tex"], 2e-3, "g_tex")
+        if kw["filter_mode"] == "nearest":       # the linear modes' g_tex is corrupted in the reference on sm_100a (see above)
+            assert_grad_close(gr["g_tex"], g["g_tex"], 1e-5, "g_tex")
         if "g_uv" in g:
             assert_close(gr["g_uv"], g["g_uv"], 1e-3, 1e-3, "g_uv", max_bad_frac=5e-3)
         if "g_uv_da" in g:

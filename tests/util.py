@@ -43,3 +43,35 @@ def assert_grad_close(g, g_ref, rel=1e-4, name=""):
     scale = max(float(np.abs(g_ref).max()), 1e-30)
     err = float(np.abs(g - g_ref).max())
     assert err <= rel * scale, "%s: max err %.3g vs scale %.3g (rel %.3g > %g)" % (name, err, scale, err / scale, rel)
+
+
+def oracle_chain(c, n, with_tex, dy, max_mip_level=-1):
+    """Whole pipeline on the CPU oracle: rasterize -> interpolate -> (texture) -> antialias, forward and backward.
+    Returns (rast, color, out, grads dict) with the same leaves as the torch pipelines in the tests / bench."""
+    import oracle
+    pos, tri = c["pos"][:n], c["tri"]
+    r = oracle.rasterize_fwd(pos, tri, c["res"])
+    rast, db = r["rast"], r["rast_db"]
+    if with_tex:
+        uv = c["uv"][None]
+        texc, texd = oracle.interpolate_fwd(uv, rast, c["uv_idx"], db, "all")
+        mip = oracle.texture_construct_mip(c["tex"], max_mip_level)
+        color = oracle.texture_fwd(c["tex"], texc, texd, None, mip=mip, filter_mode="linear-mipmap-linear")
+    else:
+        attr = c["attr"][None]
+        color, _ = oracle.interpolate_fwd(attr, rast, tri)
+    out, items = oracle.antialias_fwd(color, rast, pos, tri)
+    g_color, g_pos = oracle.antialias_grad(color, rast, pos, tri, dy, items)
+    grads = {}
+    if with_tex:
+        tg = oracle.texture_grad(c["tex"], texc, g_color, texd, None, mip=mip, filter_mode="linear-mipmap-linear")
+        grads["tex"] = tg["g_tex"]
+        g_uv, g_rast, g_db = oracle.interpolate_grad(uv, rast, c["uv_idx"], tg["g_uv"], db, tg["g_uv_da"], "all")
+        grads["uv"] = g_uv[0]
+        g_pos = g_pos + oracle.rasterize_grad(pos, tri, rast, g_rast, g_db)
+    else:
+        g_attr, g_rast, _ = oracle.interpolate_grad(attr, rast, tri, g_color)
+        grads["attr"] = g_attr[0]
+        g_pos = g_pos + oracle.rasterize_grad(pos, tri, rast, g_rast, None)
+    grads["pos"] = g_pos
+    return rast, color, out, grads
