@@ -215,19 +215,34 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_fwd_kernel(const TexParam
 // ------------------------------------------------------------------------------------------------
 // Backward
 
-// Add w * dy[0..C) to the padded texel gradient at index tc of one pyramid level, 4 channels per vector reduction.
-static __device__ __forceinline__ void accum_texel(float* g, int tc, int C, int Cp, float w, const float* dy)
+// Warp-cooperative texel-gradient accumulation.  Every lane of the warp calls this (inactive lanes pass tc = -1).
+// Lanes that hit the same texel of the same level in consecutive pixels (magnified textures, constant uv such as the
+// background) are summed with shuffles first, so a texel receives one 128-bit vector reduction (REDG.E.ADD.F32x4) per
+// run instead of one atomic per pixel and channel; 32 pixels on one texel cost one reduction, not 32 serialised ones.
+static __device__ __forceinline__ void accum_texel_warp(float* g, int level, int tc, int C, int Cp, float w, const float* dy)
 {
-    if (tc < 0) return;
-    float* q = g + (size_t)tc * Cp;
+    int key = (tc >= 0) ? (tc ^ (level << 27)) : -1;
+    WarpRuns runs = warp_runs(key);
+    const bool dup = (runs.heads != 0xffffffffu);       // warp-uniform: any two neighbouring lanes on the same texel?
+    float* q = g + (size_t)(tc >= 0 ? tc : 0) * Cp;
     for (int k = 0; k < Cp; k += 4)
     {
-        float4 v;
-        v.x = w * dy[k];
-        v.y = (k + 1 < C) ? w * dy[k + 1] : 0.f;
-        v.z = (k + 2 < C) ? w * dy[k + 2] : 0.f;
-        v.w = (k + 3 < C) ? w * dy[k + 3] : 0.f;
-        red_add4(q + k, v);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tc >= 0)
+        {
+            v.x = w * dy[k];
+            v.y = (k + 1 < C) ? w * dy[k + 1] : 0.f;
+            v.z = (k + 2 < C) ? w * dy[k + 2] : 0.f;
+            v.w = (k + 3 < C) ? w * dy[k + 3] : 0.f;
+        }
+        if (dup)
+        {
+            v.x = warp_run_sum(v.x, runs);
+            if (k + 1 < C) v.y = warp_run_sum(v.y, runs);
+            if (k + 2 < C) v.z = warp_run_sum(v.z, runs);
+            if (k + 3 < C) v.w = warp_run_sum(v.w, runs);
+        }
+        if (runs.is_head && tc >= 0) red_add4(q + k, v);
     }
 }
 
@@ -250,78 +265,97 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_grad_kernel(const TexPara
             coop_load(s_dy, p.dy + pbase * C, npx * C, tid);
             __syncthreads();
         }
-        if (tid < npx)
+        const bool inb = tid < npx;
+        const float* pDy = p.staged ? (s_dy + tid * C) : (p.dy + (inb ? pidx : pbase) * C);
+
+        // ---- per-pixel setup (lanes without work keep tc = -1 and flow through the warp-cooperative part)
+        bool act = false;
+        if (inb)
         {
-            const float* pDy = p.staged ? (s_dy + tid * C) : (p.dy + pidx * C);
             unsigned dmax = 0u;
             for (int i = 0; i < C; i++) dmax |= __float_as_uint(pDy[i]);
-
-            float gu = 0.f, gv = 0.f, df = 0.f;
-            float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (__uint_as_float(dmax) != 0.f)        // zero incoming gradient: only the zero stores below (texture_kernel.cu:922-971)
+            act = (__uint_as_float(dmax) != 0.f);       // zero incoming gradient: only the zero stores below (texture_kernel.cu:922-971)
+        }
+        int level0 = 0, level1 = 0; float flevel = 0.f;
+        int4 tc0 = make_int4(-1, -1, -1, -1), tc1 = make_int4(-1, -1, -1, -1);
+        float2 uv0 = make_float2(0.f, 0.f), uv1 = make_float2(0.f, 0.f);
+        float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool two = false;
+        float f0 = 1.f;
+        if (act)
+        {
+            int pz = (int)(pidx / hw);
+            int tz = (p.texD == 1) ? 0 : pz;
+            float2 uv = ld_stream_f2((const float2*)p.uv + pidx);
+            if (p.filter == B200DR_FILTER_NEAREST)
             {
-                int pz = (int)(pidx / hw);
-                int tz = (p.texD == 1) ? 0 : pz;
-                float2 uv = ld_stream_f2((const float2*)p.uv + pidx);
-                if (p.filter == B200DR_FILTER_NEAREST)
+                tc0.x = index_nearest(p, uv.x, uv.y, tz);
+            }
+            else
+            {
+                mip_level<true>(p, pidx, level0, level1, flevel, dw);
+                uv0 = index_linear(p, uv.x, uv.y, tz, level0, tc0);
+                two = trilinear && (flevel > 0.f);
+                f0 = trilinear ? (1.f - flevel) : 1.f;
+                if (two) uv1 = index_linear(p, uv.x, uv.y, tz, level1, tc1);
+            }
+        }
+
+        // ---- texel gradients (warp-uniform control flow)
+        if (__any_sync(0xffffffffu, act))
+        {
+            if (p.filter == B200DR_FILTER_NEAREST)
+            {
+                accum_texel_warp(p.gpad[0], 0, tc0.x, C, Cp, 1.f, pDy);
+            }
+            else
+            {
+                float uv011 = uv0.x * uv0.y, uv010 = uv0.x - uv011, uv001 = uv0.y - uv011, uv000 = 1.f - uv0.x - uv001;
+                float* g0 = p.gpad[level0];
+                accum_texel_warp(g0, level0, tc0.x, C, Cp, uv000 * f0, pDy);
+                accum_texel_warp(g0, level0, tc0.y, C, Cp, uv010 * f0, pDy);
+                accum_texel_warp(g0, level0, tc0.z, C, Cp, uv001 * f0, pDy);
+                accum_texel_warp(g0, level0, tc0.w, C, Cp, uv011 * f0, pDy);
+                if (__any_sync(0xffffffffu, two))
                 {
-                    int tc = index_nearest(p, uv.x, uv.y, tz);
-                    accum_texel(p.gpad[0], tc, C, Cp, 1.f, pDy);
+                    float uv111 = uv1.x * uv1.y, uv110 = uv1.x - uv111, uv101 = uv1.y - uv111, uv100 = 1.f - uv1.x - uv101;
+                    float* g1 = p.gpad[level1];
+                    accum_texel_warp(g1, level1, two ? tc1.x : -1, C, Cp, uv100 * flevel, pDy);
+                    accum_texel_warp(g1, level1, two ? tc1.y : -1, C, Cp, uv110 * flevel, pDy);
+                    accum_texel_warp(g1, level1, two ? tc1.z : -1, C, Cp, uv101 * flevel, pDy);
+                    accum_texel_warp(g1, level1, two ? tc1.w : -1, C, Cp, uv111 * flevel, pDy);
                 }
-                else
+            }
+        }
+
+        // ---- uv and mip-level gradients
+        if (inb)
+        {
+            float gu = 0.f, gv = 0.f, df = 0.f;
+            if (act && p.filter != B200DR_FILTER_NEAREST)
+            {
+                const float* t0 = p.tex[level0];
+                const float* t1 = p.tex[level1];
+                float sclu0 = (float)lvl_w(p, level0), sclv0 = (float)lvl_h(p, level0);
+                float sclu1 = (float)lvl_w(p, level1), sclv1 = (float)lvl_h(p, level1);
+                for (int i = 0; i < C; i++)
                 {
-                    int level0, level1; float flevel;
-                    mip_level<true>(p, pidx, level0, level1, flevel, dw);
-                    int4 tc0;
-                    float2 uv0 = index_linear(p, uv.x, uv.y, tz, level0, tc0);
-                    const float* t0 = p.tex[level0];
-                    float uv011 = uv0.x * uv0.y, uv010 = uv0.x - uv011, uv001 = uv0.y - uv011, uv000 = 1.f - uv0.x - uv001;
-                    float sclu0 = (float)lvl_w(p, level0), sclv0 = (float)lvl_h(p, level0);
-                    bool two = trilinear && (flevel > 0.f);
-                    float f0 = trilinear ? (1.f - flevel) : 1.f;
-
-                    // texel gradients, level 0 of the pair
-                    accum_texel(p.gpad[level0], tc0.x, C, Cp, uv000 * f0, pDy);
-                    accum_texel(p.gpad[level0], tc0.y, C, Cp, uv010 * f0, pDy);
-                    accum_texel(p.gpad[level0], tc0.z, C, Cp, uv001 * f0, pDy);
-                    accum_texel(p.gpad[level0], tc0.w, C, Cp, uv011 * f0, pDy);
-
-                    int4 tc1 = make_int4(-1, -1, -1, -1);
-                    float2 uv1 = make_float2(0.f, 0.f);
-                    const float* t1 = p.tex[0];
-                    float sclu1 = 0.f, sclv1 = 0.f;
+                    float dy = pDy[i];
+                    float dy0 = f0 * dy;
+                    float a00 = texel(t0, tc0.x, C, i), a10 = texel(t0, tc0.y, C, i), a01 = texel(t0, tc0.z, C, i), a11 = texel(t0, tc0.w, C, i);
+                    float ad = (a11 + a00 - a10 - a01);
+                    gu += dy0 * ((a10 - a00) + uv0.y * ad) * sclu0;
+                    gv += dy0 * ((a01 - a00) + uv0.x * ad) * sclv0;
                     if (two)
                     {
-                        uv1 = index_linear(p, uv.x, uv.y, tz, level1, tc1);
-                        t1 = p.tex[level1];
-                        float uv111 = uv1.x * uv1.y, uv110 = uv1.x - uv111, uv101 = uv1.y - uv111, uv100 = 1.f - uv1.x - uv101;
-                        sclu1 = (float)lvl_w(p, level1); sclv1 = (float)lvl_h(p, level1);
-                        accum_texel(p.gpad[level1], tc1.x, C, Cp, uv100 * flevel, pDy);
-                        accum_texel(p.gpad[level1], tc1.y, C, Cp, uv110 * flevel, pDy);
-                        accum_texel(p.gpad[level1], tc1.z, C, Cp, uv101 * flevel, pDy);
-                        accum_texel(p.gpad[level1], tc1.w, C, Cp, uv111 * flevel, pDy);
-                    }
-
-                    // uv and mip-level gradients
-                    for (int i = 0; i < C; i++)
-                    {
-                        float dy = pDy[i];
-                        float dy0 = f0 * dy;
-                        float a00 = texel(t0, tc0.x, C, i), a10 = texel(t0, tc0.y, C, i), a01 = texel(t0, tc0.z, C, i), a11 = texel(t0, tc0.w, C, i);
-                        float ad = (a11 + a00 - a10 - a01);
-                        gu += dy0 * ((a10 - a00) + uv0.y * ad) * sclu0;
-                        gv += dy0 * ((a01 - a00) + uv0.x * ad) * sclv0;
-                        if (two)
-                        {
-                            float dy1 = flevel * dy;
-                            float b00 = texel(t1, tc1.x, C, i), b10 = texel(t1, tc1.y, C, i), b01 = texel(t1, tc1.z, C, i), b11 = texel(t1, tc1.w, C, i);
-                            float bd = (b11 + b00 - b10 - b01);
-                            gu += dy1 * ((b10 - b00) + uv1.y * bd) * sclu1;
-                            gv += dy1 * ((b01 - b00) + uv1.x * bd) * sclv1;
-                            float a = bilerp(a00, a10, a01, a11, uv0);
-                            float b = bilerp(b00, b10, b01, b11, uv1);
-                            df += (b - a) * dy;
-                        }
+                        float dy1 = flevel * dy;
+                        float b00 = texel(t1, tc1.x, C, i), b10 = texel(t1, tc1.y, C, i), b01 = texel(t1, tc1.z, C, i), b11 = texel(t1, tc1.w, C, i);
+                        float bd = (b11 + b00 - b10 - b01);
+                        gu += dy1 * ((b10 - b00) + uv1.y * bd) * sclu1;
+                        gv += dy1 * ((b01 - b00) + uv1.x * bd) * sclv1;
+                        float a = bilerp(a00, a10, a01, a11, uv0);
+                        float b = bilerp(b00, b10, b01, b11, uv1);
+                        df += (b - a) * dy;
                     }
                 }
             }

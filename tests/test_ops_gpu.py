@@ -337,7 +337,7 @@ def test_chain_vs_reference_and_oracle(dr, ctx, cfg):
     dy = _rand_like(tuple(a_out.shape), 19)
     (a_out * cu(dy)).sum().backward()
     o_rast, o_color, o_out, o_grads = oracle_chain(c, n, with_tex, dy, max_mip_level=8)
-    assert np.array_equal(a_rast[..., 3].cpu().numpy(), o_rast[..., 3])
+    assert np.array_equal(a_rast[..., 3].detach().cpu().numpy(), o_rast[..., 3])
     assert_close(a_color.detach().cpu().numpy(), o_color, 5e-5, 1e-4, "color vs oracle", max_bad_frac=3e-3)
     assert_close(a_out.detach().cpu().numpy(), o_out, 5e-5, 1e-4, "aa out vs oracle", max_bad_frac=3e-3)
     for k in a_leaves:
