@@ -122,16 +122,25 @@ int b200dr_antialias_grad(const float* color, const float* rast, const float* po
                           float* g_color, float* g_pos, void* stream);
 
 /* ---- texture (2-D) --------------------------------------------------------------------- */
-/* Mip layout identical to calculateMipInfo (csrc/common/texture.cpp:62-102).  Returns the number of floats in
- * the packed mip stack, fills offsets[0..16] and *max_level; returns -1 if an odd extent cannot be halved. */
+/* Texels are consumed from a CHANNEL-PADDED pyramid: every level (0 = base texture .. max_level) holds
+ * Cp = (C + 3) & ~3 floats per texel, so a bilinear tap is one 128-bit load per corner.  The caller pads level 0 with
+ * b200dr_texture_pad (when C % 4 != 0) and builds or pads the mip levels; all level pointers are 16-byte aligned. */
+
+/* Mip layout identical to calculateMipInfo (csrc/common/texture.cpp:62-102) for a texture with C floats per texel
+ * (pass Cp to lay out the padded pyramid).  Returns the number of floats in the packed mip stack, fills
+ * offsets[0..16] and *max_level; returns -1 if an odd extent cannot be halved. */
 long long b200dr_texture_mip_info(int texW, int texH, int texD, int C, int max_mip_level, int* offsets, int* max_level);
 
-/* Replaces texture_construct_mip (torch_texture.cpp:98-169, texture_kernel.cu:644-704). */
+/* dst[t][0..Cp) = src[t][0..C), zero padded; ntexels = texD*texH*texW of that level. */
+int b200dr_texture_pad(const float* src, float* dst, long long ntexels, int C, void* stream);
+
+/* Replaces texture_construct_mip (torch_texture.cpp:98-169, texture_kernel.cu:644-704) on padded data:
+ * tex = padded level 0, mip = padded packed stack laid out by b200dr_texture_mip_info(.., Cp, ..), C = Cp. */
 int b200dr_texture_construct_mip(const float* tex, float* mip, int texW, int texH, int texD, int C,
                                  const int* offsets, int max_level, void* stream);
 
 /* Replaces texture_fwd / texture_fwd_mip (torch_texture.cpp:174-416, texture_kernel.cu:709-800), 2-D modes.
- *   mip_ptrs[1..max_level] = device pointers of mip levels (packed stack or custom list); mip_ptrs[0] ignored. */
+ *   tex = padded level 0; mip_ptrs[1..max_level] = padded mip levels (mip_ptrs[0] ignored); C = real channel count. */
 int b200dr_texture_fwd(const float* tex, const float* const* mip_ptrs, int max_level,
                        const float* uv, const float* uv_da, const float* mip_level_bias,
                        int N, int H, int W, int texD, int texH, int texW, int C,
@@ -140,9 +149,9 @@ int b200dr_texture_fwd(const float* tex, const float* const* mip_ptrs, int max_l
 /* Replaces texture_grad_{nearest,linear,linear_mipmap_nearest,linear_mipmap_linear}
  * (torch_texture.cpp:421-716, texture_kernel.cu:843-1154), 2-D modes.
  *   scratch: b200dr_texture_grad_scratch_bytes() bytes (channel-padded gradient pyramid, zeroed here).
- *   g_tex (shape of tex) is fully written.  pull_mips != 0 (internal mip stack): mip-level gradients are pulled
+ *   tex / mip_ptrs: padded levels as in b200dr_texture_fwd.  g_tex (UNPADDED, shape of the user's tex) is fully written.  pull_mips != 0 (internal mip stack): mip-level gradients are pulled
  *   down into g_tex and g_mip_ptrs is ignored; pull_mips == 0 with max_level > 0 (custom mip stack): level l's
- *   gradient is written to g_mip_ptrs[l] (1..max_level).
+ *   gradient is written, UNPADDED, to g_mip_ptrs[l] (1..max_level).
  *   g_uv [N,H,W,2] (NULL for nearest), g_uv_da [N,H,W,4] / g_bias [N,H,W] may be NULL. */
 size_t b200dr_texture_grad_scratch_bytes(int texD, int texH, int texW, int C, int max_level);
 int b200dr_texture_grad(const float* tex, const float* const* mip_ptrs, int max_level,

@@ -30,6 +30,7 @@ SIGNATURES = {
     "b200dr_antialias_fwd": (_int, [_vp, _vp, _vp, _vp, _vp] + [_int] * 7 + [_vp, _vp, _vp, _vp]),
     "b200dr_antialias_grad": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp] + [_int] * 7 + [_vp, _vp, _vp]),
     "b200dr_texture_mip_info": (_c.c_longlong, [_int, _int, _int, _int, _int, _c.POINTER(_int), _c.POINTER(_int)]),
+    "b200dr_texture_pad": (_int, [_vp, _vp, _c.c_longlong, _int, _vp]),
     "b200dr_texture_construct_mip": (_int, [_vp, _vp, _int, _int, _int, _int, _c.POINTER(_int), _int, _vp]),
     "b200dr_texture_fwd": (_int, [_vp, _c.POINTER(_vp), _int, _vp, _vp, _vp] + [_int] * 9 + [_vp, _vp]),
     "b200dr_texture_grad_scratch_bytes": (_sz, [_int, _int, _int, _int, _int]),

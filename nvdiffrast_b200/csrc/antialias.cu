@@ -120,66 +120,96 @@ struct AAParams
 // ------------------------------------------------------------------------------------------------
 // Dense pass: out = color, find id discontinuities (csrc/common/antialias.cu:165-214).
 
-#define AA_TILE_W 32
-#define AA_TILE_H 8
+// A thread owns a vertical strip of AA_ROWS pixels of one column (a warp: 32 columns x AA_ROWS rows), a CTA of 8 warps a
+// 128 x 16 pixel tile.  All of a thread's loads (AA_ROWS + 1 triangle ids, AA_ROWS colour vectors) are issued before the
+// first use, the "next row" neighbour is the thread's own next register, the right neighbour a shuffle; no shared memory,
+// no block barrier, one atomic per warp for all the work items of its 32 x AA_ROWS pixels.
+#define AA_ROWS   8
+#define AA_WARPS_X 4
+#define AA_WARPS_Y 2
+#define AA_TILE_W (32 * AA_WARPS_X)
+#define AA_TILE_H (AA_ROWS * AA_WARPS_Y)
 
-__global__ void __launch_bounds__(AA_TILE_W * AA_TILE_H) aa_discontinuity_kernel(const AAParams p)
+__global__ void __launch_bounds__(256) aa_discontinuity_kernel(const AAParams p)
 {
-    __shared__ float s_id[AA_TILE_H + 1][AA_TILE_W];
-    const int lane = threadIdx.x, ty = threadIdx.y;
-    const int px = blockIdx.x * AA_TILE_W + lane;
-    const int py = blockIdx.y * AA_TILE_H + ty;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * AA_TILE_W + (warp % AA_WARPS_X) * 32;       // first column of this warp
+    const int y0 = blockIdx.y * AA_TILE_H + (warp / AA_WARPS_X) * AA_ROWS;   // first row of this warp
     const int pz = blockIdx.z;
-    const bool inb = (px < p.W) && (py < p.H);
-    const size_t row = ((size_t)pz * p.H + min(py, p.H - 1)) * p.W;         // clamped so that address math stays valid
+    const int px = x0 + lane;
+    if (x0 >= p.W || y0 >= p.H) return;                                     // whole warp outside the image
+    const bool colin = px < p.W;
+    const size_t img = (size_t)pz * p.H * p.W;
+    const float* idp = p.rast + (img + (size_t)y0 * p.W + min(px, p.W - 1)) * 4 + 3;
 
-    // ---- color -> out for this warp's row segment (contiguous floats; 128-bit when the layout allows)
-    if (py < p.H)
+    // ---- issue every load of this strip: ids of rows y0 .. y0+AA_ROWS (clamped), right-hand column for lane 31, colours
+    float id[AA_ROWS + 1], idr[AA_ROWS];
+    #pragma unroll
+    for (int r = 0; r <= AA_ROWS; r++)
     {
-        int x0 = blockIdx.x * AA_TILE_W;
-        int nflt = min(AA_TILE_W, p.W - x0) * p.C;
-        size_t base = (row + x0) * p.C;
-        if (p.vec_ok && ((p.W * p.C) & 3) == 0 && ((x0 * p.C) & 3) == 0)
+        int y = min(y0 + r, p.H - 1);
+        id[r] = __ldg(idp + (size_t)(y - y0) * p.W * 4);
+    }
+    const bool need_right = (lane == 31) && (px < p.W - 1);
+    #pragma unroll
+    for (int r = 0; r < AA_ROWS; r++)
+    {
+        idr[r] = 0.f;
+        if (need_right && y0 + r < p.H) idr[r] = __ldg(idp + (size_t)r * p.W * 4 + 4);
+    }
+
+    const int nflt = min(32, p.W - x0) * p.C;                               // floats of one row segment of this warp
+    const bool vec = p.vec_ok && ((p.W * p.C) & 3) == 0 && ((x0 * p.C) & 3) == 0;
+    if (vec && nflt <= 128)
+    {
+        float4 c[AA_ROWS];
+        const int q = lane * 4;
+        #pragma unroll
+        for (int r = 0; r < AA_ROWS; r++)
+            if (y0 + r < p.H && q < nflt) c[r] = ld_stream_f4((const float4*)(p.color + (img + (size_t)(y0 + r) * p.W + x0) * p.C) + lane);
+        #pragma unroll
+        for (int r = 0; r < AA_ROWS; r++)
+            if (y0 + r < p.H && q < nflt) st_stream_f4((float4*)(p.out + (img + (size_t)(y0 + r) * p.W + x0) * p.C) + lane, c[r]);
+    }
+    else
+    {
+        for (int r = 0; r < AA_ROWS && y0 + r < p.H; r++)
         {
-            const float4* src = (const float4*)(p.color + base);
-            float4* dst = (float4*)(p.out + base);
-            for (int i = lane; i < (nflt >> 2); i += 32) st_stream_f4(dst + i, ld_stream_f4(src + i));
-        }
-        else
-        {
-            for (int i = lane; i < nflt; i += 32) st_stream_f(p.out + base + i, ld_stream_f(p.color + base + i));
+            size_t base = (img + (size_t)(y0 + r) * p.W + x0) * p.C;
+            if (vec) for (int i = lane; i < (nflt >> 2); i += 32) st_stream_f4((float4*)(p.out + base) + i, ld_stream_f4((const float4*)(p.color + base) + i));
+            else     for (int i = lane; i < nflt; i += 32) st_stream_f(p.out + base + i, ld_stream_f(p.color + base + i));
         }
     }
 
-    // ---- triangle ids of the tile plus the row above it
-    float tri0 = 0.f;
-    if (inb) tri0 = __ldg(p.rast + (row + px) * 4 + 3);
-    s_id[ty][lane] = tri0;
-    if (ty == AA_TILE_H - 1)
+    // ---- discontinuities (csrc/common/antialias.cu:165-214): right neighbour (clamped at the image edge), next row
+    unsigned m1[AA_ROWS], m2[AA_ROWS];
+    int total = 0;
+    #pragma unroll
+    for (int r = 0; r < AA_ROWS; r++)
     {
-        float up = tri0;
-        if (inb && py < p.H - 1) up = __ldg(p.rast + (row + p.W + px) * 4 + 3);
-        s_id[AA_TILE_H][lane] = up;
+        float right = __shfl_down_sync(0xffffffffu, id[r], 1);
+        if (lane == 31) right = idr[r];
+        bool rowin = (y0 + r < p.H);
+        bool f1 = colin && rowin && (px < p.W - 1) && (right != id[r]);
+        bool f2 = colin && rowin && (y0 + r < p.H - 1) && (id[r + 1] != id[r]);
+        m1[r] = __ballot_sync(0xffffffffu, f1);
+        m2[r] = __ballot_sync(0xffffffffu, f2);
+        total += __popc(m1[r]) + __popc(m2[r]);
     }
-    float tri1 = __shfl_down_sync(0xffffffffu, tri0, 1);                   // right neighbour
-    if (lane == 31 && inb && px < p.W - 1) tri1 = __ldg(p.rast + (row + px + 1) * 4 + 3);
-    if (!inb || px >= p.W - 1) tri1 = tri0;                                // clamp at the image edge
-    __syncthreads();
-    float tri2 = tri0;
-    if (inb && py < p.H - 1) tri2 = s_id[ty + 1][lane];                    // neighbour in the next row
-
-    // ---- append work items, one atomic per warp
-    bool f1 = inb && (tri1 != tri0), f2 = inb && (tri2 != tri0);
-    unsigned m1 = __ballot_sync(0xffffffffu, f1), m2 = __ballot_sync(0xffffffffu, f2);
-    if ((m1 | m2) == 0) return;
-    int n1 = __popc(m1), total = n1 + __popc(m2);
+    if (total == 0) return;                                                  // warp-uniform
     int base = 0;
     if (lane == 0) base = atomicAdd(p.counters, total);
     base = __shfl_sync(0xffffffffu, base, 0);
-    unsigned lt = (1u << lane) - 1u;
-    int pxy = px | (py << 16);
-    if (f1) p.items[base + __popc(m1 & lt)] = make_int4(pxy, pz, 0, 0);
-    if (f2) p.items[base + n1 + __popc(m2 & lt)] = make_int4(pxy, pz, 1 << AA_FLAG_DOWN_BIT, 0);
+    const unsigned lt = (1u << lane) - 1u;
+    #pragma unroll
+    for (int r = 0; r < AA_ROWS; r++)
+    {
+        int pxy = px | ((y0 + r) << 16);
+        if ((m1[r] >> lane) & 1u) p.items[base + __popc(m1[r] & lt)] = make_int4(pxy, pz, 0, 0);
+        base += __popc(m1[r]);
+        if ((m2[r] >> lane) & 1u) p.items[base + __popc(m2[r] & lt)] = make_int4(pxy, pz, 1 << AA_FLAG_DOWN_BIT, 0);
+        base += __popc(m2[r]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -466,7 +496,7 @@ extern "C" int b200dr_antialias_fwd(const float* color, const float* rast, const
     p.wings = (const int4*)wings; p.out = out; p.vec_ok = B200DR_ALIGNED16(color) && B200DR_ALIGNED16(out); p.items = (int4*)work_items; p.counters = work_counters;
     cudaMemsetAsync(work_counters, 0, 4 * sizeof(int), stream);
     dim3 grid((W + AA_TILE_W - 1) / AA_TILE_W, (H + AA_TILE_H - 1) / AA_TILE_H, N);
-    aa_discontinuity_kernel<<<grid, dim3(AA_TILE_W, AA_TILE_H), 0, stream>>>(p);
+    aa_discontinuity_kernel<<<grid, 256, 0, stream>>>(p);
     B200DR_CHECK_LAUNCH("antialias_fwd(discontinuity)");
     aa_analysis_kernel<<<b200dr_num_sms() * 8, 256, 0, stream>>>(p);
     B200DR_CHECK_LAUNCH("antialias_fwd(analysis)");

@@ -78,6 +78,79 @@ static __device__ __forceinline__ void st_stream_u4(uint4* p, uint4 v)
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// 256-bit accesses (LDG.E.256 / STG.E.256, new on sm_100): two float4 pixels per instruction, and the only access
+// width that accepts an L2 eviction priority.  Address must be 32-byte aligned.
+static __device__ __forceinline__ void ld_stream_f8(const float* p, float4& a, float4& b)
+{
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+static __device__ __forceinline__ void st_stream_f8(float* p, float4 a, float4 b)
+{
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-cooperative AoS access: lane l owns K consecutive floats at base[l*K .. l*K+K) (32 pixels x K channels,
+// contiguous).  K = 1, 2, 4, 8 map to one vector access per lane.  Other K go through a warp-private shared-memory
+// transpose so that global memory still sees full 128-bit coalesced accesses; `s` points to >= 32*K floats owned by this
+// warp (16-byte aligned).  `full`: all 32 pixels valid and `base` 16-byte aligned; otherwise a scalar path is taken.
+
+template <int K>
+static __device__ __forceinline__ void warp_store_aos(float* base, const float (&v)[K], int lane, bool valid, bool full, float* s)
+{
+    if (K == 1) { if (valid) st_stream_f(base + lane, v[0]); }
+    else if (K == 2) { if (valid) st_stream_f2((float2*)base + lane, make_float2(v[0], v[1])); }
+    else if (K == 4) { if (valid) st_stream_f4((float4*)base + lane, make_float4(v[0], v[1], v[2], v[3])); }
+    else if (K == 8) { if (valid) st_stream_f8(base + 8 * lane, make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7])); }
+    else if (full)
+    {
+        #pragma unroll
+        for (int i = 0; i < K; i++) s[lane * K + i] = v[i];
+        __syncwarp();
+        #pragma unroll
+        for (int j = 0; j < (K * 32 + 127) / 128; j++)
+        {
+            int q = lane + 32 * j;
+            if (q * 4 < K * 32) st_stream_f4((float4*)base + q, *(const float4*)(s + 4 * q));
+        }
+        __syncwarp();
+    }
+    else if (valid)
+    {
+        #pragma unroll
+        for (int i = 0; i < K; i++) st_stream_f(base + lane * K + i, v[i]);
+    }
+}
+
+template <int K>
+static __device__ __forceinline__ void warp_load_aos(const float* base, float (&v)[K], int lane, bool valid, bool full, float* s)
+{
+    if (K == 1) { if (valid) v[0] = ld_stream_f(base + lane); }
+    else if (K == 2) { if (valid) { float2 t = ld_stream_f2((const float2*)base + lane); v[0] = t.x; v[1] = t.y; } }
+    else if (K == 4) { if (valid) { float4 t = ld_stream_f4((const float4*)base + lane); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } }
+    else if (K == 8) { if (valid) { float4 a, b; ld_stream_f8(base + 8 * lane, a, b); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; } }
+    else if (full)
+    {
+        #pragma unroll
+        for (int j = 0; j < (K * 32 + 127) / 128; j++)
+        {
+            int q = lane + 32 * j;
+            if (q * 4 < K * 32) *(float4*)(s + 4 * q) = ld_stream_f4((const float4*)base + q);
+        }
+        __syncwarp();
+        #pragma unroll
+        for (int i = 0; i < K; i++) v[i] = s[lane * K + i];
+        __syncwarp();
+    }
+    else if (valid)
+    {
+        #pragma unroll
+        for (int i = 0; i < K; i++) v[i] = ld_stream_f(base + lane * K + i);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Warp-level segmented ("run") reduction.
 //

@@ -248,6 +248,241 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_kernel(const Inte
     }
 }
 
+// ================================================================================================
+// Fast paths: A in {1,2,3,4}, pixel differentials for none or all attributes.
+//
+// Warp-autonomous: a warp owns groups of 32 consecutive pixels, two groups in flight per iteration, no block barriers in
+// the loop.  Channel count is a template parameter, so attribute rows live in registers and every per-pixel tensor is
+// moved with one vector access per lane (K = 1, 2, 4, 8 floats) or through a warp-private shared-memory transpose
+// (K = 3, 6).  Per-pixel tensors that only matter under geometry (rast_db, dy, dda) are fetched after the triangle id is
+// known: empty regions cost 16 bytes per pixel instead of the full algorithmic traffic.
+// ================================================================================================
+
+#define IPF_UNROLL 2
+
+template <int A>
+static __device__ __forceinline__ void load_row(const float* a, float (&v)[A])
+{
+    if (A == 2) { float2 t = __ldg((const float2*)a); v[0] = t.x; v[1] = t.y; }
+    else if (A == 4) { float4 t = __ldg((const float4*)a); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else { _Pragma("unroll") for (int i = 0; i < A; i++) v[i] = __ldg(a + i); }
+}
+
+template <int A, bool DA>
+__global__ void __launch_bounds__(IP_THREADS) interpolate_fwd_fast(const InterpParams p)
+{
+    constexpr int SK = (A == 3) ? (DA ? 6 : 3) : 1;                    // staging floats per pixel (only K = 3 / 6 need it)
+    __shared__ __align__(16) float s_stage[IP_THREADS / 32][32 * SK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.y;
+    const int hw = p.H * p.W;
+    const int groups = (hw + 31) >> 5;
+    const int wstride = gridDim.x * (IP_THREADS / 32);
+    const size_t img = (size_t)n * hw;
+    const bool row_aligned = (((size_t)hw * A) & 3) == 0;
+
+    for (int g0 = blockIdx.x * (IP_THREADS / 32) + warp; g0 < groups; g0 += IPF_UNROLL * wstride)
+    {
+        float4 r[IPF_UNROLL], db[IPF_UNROLL];
+        bool inb[IPF_UNROLL], valid[IPF_UNROLL];
+        int vi0[IPF_UNROLL], vi1[IPF_UNROLL], vi2[IPF_UNROLL];
+        #pragma unroll
+        for (int u = 0; u < IPF_UNROLL; u++)
+        {
+            int px = (g0 + u * wstride) * 32 + lane;
+            inb[u] = (g0 + u * wstride < groups) && (px < hw);
+            r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (inb[u]) r[u] = ld_stream_f4((const float4*)p.rast + img + px);
+        }
+        #pragma unroll
+        for (int u = 0; u < IPF_UNROLL; u++)
+        {
+            int px = (g0 + u * wstride) * 32 + lane;
+            vi0[u] = vi1[u] = vi2[u] = 0;
+            valid[u] = inb[u] && pixel_triangle(p, r[u].w, n, vi0[u], vi1[u], vi2[u]);
+            db[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (DA && valid[u]) db[u] = ld_stream_f4((const float4*)p.rast_db + img + px);
+        }
+        #pragma unroll
+        for (int u = 0; u < IPF_UNROLL; u++)
+        {
+            int g = g0 + u * wstride;
+            if (g >= groups) continue;                                  // warp-uniform
+            float o[A], oda[DA ? 2 * A : 1];
+            #pragma unroll
+            for (int i = 0; i < A; i++) o[i] = 0.f;
+            #pragma unroll
+            for (int i = 0; i < (DA ? 2 * A : 1); i++) oda[i] = 0.f;
+            if (valid[u])
+            {
+                float a0[A], a1[A], a2[A];
+                load_row<A>(p.attr + (size_t)vi0[u] * A, a0);
+                load_row<A>(p.attr + (size_t)vi1[u] * A, a1);
+                load_row<A>(p.attr + (size_t)vi2[u] * A, a2);
+                float b0 = r[u].x, b1 = r[u].y, b2 = 1.f - r[u].x - r[u].y;
+                #pragma unroll
+                for (int i = 0; i < A; i++)
+                {
+                    o[i] = b0 * a0[i] + b1 * a1[i] + b2 * a2[i];
+                    if (DA)
+                    {
+                        float dsdu = a0[i] - a2[i], dsdv = a1[i] - a2[i];
+                        oda[2 * i] = db[u].x * dsdu + db[u].z * dsdv;
+                        oda[2 * i + 1] = db[u].y * dsdu + db[u].w * dsdv;
+                    }
+                }
+            }
+            size_t pbase = img + (size_t)g * 32;
+            bool full = row_aligned && (g * 32 + 32 <= hw);
+            warp_store_aos<A>(p.out + pbase * A, o, lane, inb[u], full, s_stage[warp]);
+            if (DA)
+            {
+                float (&od)[DA ? 2 * A : 1] = oda;
+                warp_store_aos<(DA ? 2 * A : 1)>(p.out_da + pbase * (2 * A), od, lane, inb[u], full, s_stage[warp]);
+            }
+        }
+    }
+}
+
+template <int A, bool DA>
+__global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const InterpParams p)
+{
+    extern __shared__ __align__(16) float s_dyn[];
+    constexpr int SK = (A == 3) ? (DA ? 6 : 3) : 1;
+    float* s_stage = s_dyn;                                             // [8 warps][32 * SK]
+    float* s_acc = s_dyn + (IP_THREADS / 32) * 32 * SK;                 // [V * A] when use_smem_acc
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = blockIdx.y;
+    const int hw = p.H * p.W;
+    const int groups = (hw + 31) >> 5;
+    const int wstride = gridDim.x * (IP_THREADS / 32);
+    const size_t img = (size_t)n * hw;
+    const bool row_aligned = (((size_t)hw * A) & 3) == 0;
+    const bool per_image = p.instance_mode && !p.attr_bc;
+    const int acc_n = p.V * A;
+    float* gbase = p.g_attr + (per_image ? (size_t)n * acc_n : 0);
+    float* acc = p.use_smem_acc ? s_acc : p.g_attr;
+    const int voff = (p.use_smem_acc && per_image) ? n * p.V : 0;
+    float* sw = s_stage + warp * 32 * SK;
+
+    if (p.use_smem_acc)
+    {
+        for (int i = tid; i < acc_n; i += IP_THREADS) s_acc[i] = 0.f;
+        __syncthreads();
+    }
+
+    for (int g0 = blockIdx.x * (IP_THREADS / 32) + warp; g0 < groups; g0 += IPF_UNROLL * wstride)
+    {
+        float4 r[IPF_UNROLL];
+        bool inb[IPF_UNROLL];
+        #pragma unroll
+        for (int u = 0; u < IPF_UNROLL; u++)
+        {
+            int px = (g0 + u * wstride) * 32 + lane;
+            inb[u] = (g0 + u * wstride < groups) && (px < hw);
+            r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (inb[u]) r[u] = ld_stream_f4((const float4*)p.rast + img + px);
+        }
+        #pragma unroll
+        for (int u = 0; u < IPF_UNROLL; u++)
+        {
+            int g = g0 + u * wstride;
+            if (g >= groups) continue;                                  // warp-uniform
+            int px = g * 32 + lane;
+            size_t pbase = img + (size_t)g * 32;
+            int vi0 = 0, vi1 = 0, vi2 = 0;
+            bool valid = inb[u] && pixel_triangle(p, r[u].w, n, vi0, vi1, vi2);
+            float4 gr = make_float4(0.f, 0.f, 0.f, 0.f), gdb = gr;
+            if (__any_sync(0xffffffffu, valid))
+            {
+                bool full = row_aligned && (g * 32 + 32 <= hw);
+                float dy[A], dda[DA ? 2 * A : 1];
+                #pragma unroll
+                for (int i = 0; i < A; i++) dy[i] = 0.f;
+                #pragma unroll
+                for (int i = 0; i < (DA ? 2 * A : 1); i++) dda[i] = 0.f;
+                float4 db = make_float4(0.f, 0.f, 0.f, 0.f);
+                // K = 3 / 6 go through the warp transpose (all lanes take part); vector widths are fetched only under geometry
+                warp_load_aos<A>(p.dy + pbase * A, dy, lane, (SK == 1) ? valid : inb[u], full, sw);
+                if (DA)
+                {
+                    warp_load_aos<(DA ? 2 * A : 1)>(p.dda + pbase * (2 * A), dda, lane, (SK == 1) ? valid : inb[u], full, sw);
+                    if (valid) db = ld_stream_f4((const float4*)p.rast_db + img + px);
+                }
+                float a0[A], a1[A], a2[A];
+                load_row<A>(p.attr + (size_t)vi0 * A, a0);             // vi* are 0 for lanes without geometry: in bounds
+                load_row<A>(p.attr + (size_t)vi1 * A, a1);
+                load_row<A>(p.attr + (size_t)vi2 * A, a2);
+                WarpRuns runs = warp_runs(valid ? float_to_triidx(r[u].w) : -1);
+                bool head = runs.is_head && valid;
+                float* ga0 = acc + (size_t)(vi0 - voff) * A;
+                float* ga1 = acc + (size_t)(vi1 - voff) * A;
+                float* ga2 = acc + (size_t)(vi2 - voff) * A;
+                float b0 = r[u].x, b1 = r[u].y, b2 = 1.f - r[u].x - r[u].y;
+                #pragma unroll
+                for (int i = 0; i < A; i++)
+                {
+                    float y = valid ? dy[i] : 0.f;
+                    float dsdu = a0[i] - a2[i], dsdv = a1[i] - a2[i];
+                    gr.x += y * dsdu;
+                    gr.y += y * dsdv;
+                    float t0 = b0 * y, t1 = b1 * y, t2 = b2 * y;
+                    if (DA)
+                    {
+                        float dsdx = valid ? dda[2 * i] : 0.f, dsdy = valid ? dda[2 * i + 1] : 0.f;
+                        gdb.x += dsdu * dsdx; gdb.y += dsdu * dsdy; gdb.z += dsdv * dsdx; gdb.w += dsdv * dsdy;
+                        float du = dsdx * db.x + dsdy * db.y;
+                        float dv = dsdx * db.z + dsdy * db.w;
+                        t0 += du; t1 += dv; t2 += -du - dv;
+                    }
+                    t0 = warp_run_sum(t0, runs); t1 = warp_run_sum(t1, runs); t2 = warp_run_sum(t2, runs);
+                    if (head) { red_add(ga0 + i, t0); red_add(ga1 + i, t1); red_add(ga2 + i, t2); }
+                }
+                if (!valid) { gr = make_float4(0.f, 0.f, 0.f, 0.f); gdb = gr; }
+            }
+            if (inb[u])
+            {
+                st_stream_f4((float4*)p.g_rast + img + px, gr);
+                if (DA) st_stream_f4((float4*)p.g_rast_db + img + px, gdb);
+            }
+        }
+    }
+
+    if (p.use_smem_acc)
+    {
+        __syncthreads();
+        for (int i = tid; i < acc_n; i += IP_THREADS)
+        {
+            float v = s_acc[i];
+            if (v != 0.f) red_add(gbase + i, v);
+        }
+    }
+}
+
+// true when the templated kernels apply
+static bool fast_ok(const InterpParams& p, bool da, const void* attr)
+{
+    if (p.A < 1 || p.A > 4) return false;
+    if (da && !(p.diff_all && p.D == p.A)) return false;
+    if (p.A == 2 && (((uintptr_t)attr) & 7)) return false;
+    if (p.A == 4 && (((uintptr_t)attr) & 15)) return false;
+    if ((size_t)p.H * p.W >= (1u << 30)) return false;
+    return true;
+}
+
+#define IP_DISPATCH(KERNEL, A_, DA_, GRID, SMEM, STREAM, P)                                  \
+    do {                                                                                    \
+        switch ((A_) * 2 + ((DA_) ? 1 : 0)) {                                               \
+        case 2: KERNEL<1, false><<<GRID, IP_THREADS, SMEM, STREAM>>>(P); break;             \
+        case 3: KERNEL<1, true ><<<GRID, IP_THREADS, SMEM, STREAM>>>(P); break;             \
+        case 4: KERNEL<2, false><<<GRID, IP_THREADS, SMEM, STREAM>>>(P); break;             \
+        case 5: KERNEL<2, true ><<<GRID, IP_THREADS, SMEM, STREAM>>>(P); break;             \
+        case 6: KERNEL<3, false><<<GRID, IP_THREADS, SMEM, STREAM>>>(P); break;             \
+        case 7: KERNEL<3, true ><<<GRID, IP_THREADS, SMEM, STREAM>>>(P); break;             \
+        case 8: KERNEL<4, false><<<GRID, IP_THREADS, SMEM, STREAM>>>(P); break;             \
+        case 9: KERNEL<4, true ><<<GRID, IP_THREADS, SMEM, STREAM>>>(P); break;             \
+        } } while (0)
+
 static int fill_params(InterpParams& p, const char* fn, const float* attr, const float* rast, const int32_t* tri, const float* rast_db,
                        int N, int H, int W, int V, int T, int A, int attr_bc, int instance_mode,
                        int diff_all, const int32_t* diff_list, int n_diff)
@@ -283,6 +518,17 @@ extern "C" int b200dr_interpolate_fwd(const float* attr, const float* rast, cons
                     da ? diff_all : 0, diff_list, da ? n_diff : 0)) return 1;
     if (!da) p.D = 0;
     p.out = out; p.out_da = out_da;
+    if (fast_ok(p, da, attr) && B200DR_ALIGNED16(out) && (!da || (((uintptr_t)out_da) & 31) == 0))
+    {
+        int groups = (int)(((size_t)H * W + 31) / 32);
+        int gx = (groups + (IP_THREADS / 32) * IPF_UNROLL - 1) / ((IP_THREADS / 32) * IPF_UNROLL);
+        int capx = (b200dr_num_sms() * 12 + N - 1) / N;
+        if (gx > capx) gx = capx;
+        if (gx < 1) gx = 1;
+        IP_DISPATCH(interpolate_fwd_fast, A, da, dim3(gx, N), 0, stream, p);
+        B200DR_CHECK_LAUNCH("interpolate_fwd()");
+        return 0;
+    }
     size_t smem = (size_t)IP_THREADS * (A + 2 * p.D) * sizeof(float);
     p.staged = smem <= 96 * 1024;
     if (!p.staged) smem = 0;
@@ -319,6 +565,34 @@ extern "C" int b200dr_interpolate_grad(const float* attr, const float* rast, con
     B200DR_CHECK(B200DR_ALIGNED16(g_rast) && B200DR_ALIGNED16(g_rast_db), "interpolate_grad(): gradient output tensors not aligned to float4");
     p.dy = dy; p.dda = dda; p.g_attr = g_attr; p.g_rast = g_rast; p.g_rast_db = g_rast_db;
 
+    if (fast_ok(p, da, attr) && B200DR_ALIGNED16(dy) && (!da || (((uintptr_t)dda) & 31) == 0))
+    {
+        size_t stage_b = (size_t)(IP_THREADS / 32) * 32 * ((A == 3) ? (da ? 6 : 3) : 1) * sizeof(float);
+        size_t acc_b = (size_t)V * A * sizeof(float);
+        p.use_smem_acc = (acc_b + stage_b <= 64 * 1024) ? 1 : 0;
+        size_t smem_f = stage_b + (p.use_smem_acc ? acc_b : 0);
+        int groups = (int)(((size_t)H * W + 31) / 32);
+        int gx = (groups + (IP_THREADS / 32) * IPF_UNROLL - 1) / ((IP_THREADS / 32) * IPF_UNROLL);
+        int capx = ((p.use_smem_acc ? b200dr_num_sms() * 4 : b200dr_num_sms() * 12) + N - 1) / N;
+        if (gx > capx) gx = capx;
+        if (gx < 1) gx = 1;
+        if (smem_f > 48 * 1024)
+        {
+            switch (A * 2 + (da ? 1 : 0)) {
+            case 2: cudaFuncSetAttribute(interpolate_grad_fast<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
+            case 3: cudaFuncSetAttribute(interpolate_grad_fast<1, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
+            case 4: cudaFuncSetAttribute(interpolate_grad_fast<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
+            case 5: cudaFuncSetAttribute(interpolate_grad_fast<2, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
+            case 6: cudaFuncSetAttribute(interpolate_grad_fast<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
+            case 7: cudaFuncSetAttribute(interpolate_grad_fast<3, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
+            case 8: cudaFuncSetAttribute(interpolate_grad_fast<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
+            case 9: cudaFuncSetAttribute(interpolate_grad_fast<4, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
+            }
+        }
+        IP_DISPATCH(interpolate_grad_fast, A, da, dim3(gx, N), smem_f, stream, p);
+        B200DR_CHECK_LAUNCH("interpolate_grad()");
+        return 0;
+    }
     size_t stage = (size_t)IP_THREADS * (A + 2 * p.D) * sizeof(float);
     p.staged = stage <= 32 * 1024;
     if (!p.staged) stage = 0;

@@ -6,6 +6,9 @@
 //
 // One kernel per direction handles every 2-D filter/boundary mode (mode switches are warp-uniform), instead of the
 // reference's 48-entry kernel table.  Per-pixel tensors are staged through shared memory for full-line accesses.
+// Texels are read from a channel-padded pyramid (Cp = C rounded up to 4 floats per texel, level 0 included) so that a
+// bilinear tap is one 128-bit load per corner instead of C scalar gathers; the front end pads level 0 per call
+// (28 bytes per texel, noise next to the per-pixel traffic) and builds / caches the padded mip levels.
 // Backward: texel gradients are accumulated into a channel-padded gradient pyramid with 128-bit vector reductions
 // (REDG.E.ADD.F32x4: one atomic per texel instead of one per texel channel), then a resolve pass pulls the mip levels
 // down to the base level and writes the gradient in the caller's channel layout.
@@ -119,34 +122,71 @@ static __device__ __forceinline__ void mip_level(const TexParams& p, size_t pidx
     flevel = fl;
 }
 
-static __device__ __forceinline__ float texel(const float* t, int tc, int C, int c) { return tc >= 0 ? __ldg(t + (size_t)tc * C + c) : 0.f; }
+// one 128-bit load: channels [k, k+4) of texel tc in a Cp-padded level (zeros for tc < 0)
+static __device__ __forceinline__ float4 texel4(const float* t, int tc, int Cp, int k)
+{
+    return tc >= 0 ? __ldg((const float4*)(t + (size_t)tc * Cp + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
 static __device__ __forceinline__ float lerpf(float a, float b, float c) { return a + c * (b - a); }
 static __device__ __forceinline__ float bilerp(float a, float b, float c, float d, float2 e) { return lerpf(lerpf(a, b, e.x), lerpf(c, d, e.x), e.y); }
+static __device__ __forceinline__ float4 bilerp4(float4 a, float4 b, float4 c, float4 d, float2 e)
+{
+    return make_float4(bilerp(a.x, b.x, c.x, d.x, e), bilerp(a.y, b.y, c.y, d.y, e), bilerp(a.z, b.z, c.z, d.z, e), bilerp(a.w, b.w, c.w, d.w, e));
+}
+static __device__ __forceinline__ void put4(float* o, int k, int C, float4 v)
+{
+    o[k] = v.x;
+    if (k + 1 < C) o[k + 1] = v.y;
+    if (k + 2 < C) o[k + 2] = v.z;
+    if (k + 3 < C) o[k + 3] = v.w;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Mip construction (texture_kernel.cu:644-704): level L from level L-1.
 
 __global__ void __launch_bounds__(256) mip_build_kernel(const float* __restrict__ in, float* __restrict__ out, int wi, int hi, int wo, int ho, int D, int C)
 {
-    size_t total = (size_t)wo * ho * D * C;
+    // C is the padded channel count (multiple of 4): one thread averages one 4-channel group of one output texel
+    const int G = C >> 2;
+    size_t total = (size_t)wo * ho * D * G;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256)
     {
-        int c = (int)(i % C); size_t t = i / C;
+        int g = (int)(i % G); size_t t = i / G;
         int x = (int)(t % wo); t /= wo;
         int y = (int)(t % ho); int z = (int)(t / ho);
-        size_t i0 = (size_t)C * ((((size_t)x + (size_t)wi * y) << 1) + (size_t)z * wi * hi) + c;
-        float v;
+        size_t i0 = (size_t)C * ((((size_t)x + (size_t)wi * y) << 1) + (size_t)z * wi * hi) + 4 * g;
+        float4 v;
         if (wi == 1 || hi == 1)
         {
             size_t i1 = (hi == 1) ? i0 + C : i0 + (size_t)C * wi;
-            v = .5f * (in[i0] + in[i1]);
+            float4 a = *(const float4*)(in + i0), b = *(const float4*)(in + i1);
+            v = make_float4(.5f * (a.x + b.x), .5f * (a.y + b.y), .5f * (a.z + b.z), .5f * (a.w + b.w));
         }
         else
         {
             size_t i1 = i0 + (size_t)C * wi;
-            v = .25f * (in[i0] + in[i0 + C] + in[i1] + in[i1 + C]);
+            float4 a = *(const float4*)(in + i0), b = *(const float4*)(in + i0 + C), c = *(const float4*)(in + i1), d = *(const float4*)(in + i1 + C);
+            v = make_float4(.25f * (a.x + b.x + c.x + d.x), .25f * (a.y + b.y + c.y + d.y), .25f * (a.z + b.z + c.z + d.z), .25f * (a.w + b.w + c.w + d.w));
         }
-        out[i] = v;
+        *(float4*)(out + (size_t)C * ((size_t)x + (size_t)wo * (y + (size_t)ho * z)) + 4 * g) = v;
+    }
+}
+
+// dst[t][0..Cp) = src[t][0..C) padded with zeros
+__global__ void __launch_bounds__(256) texture_pad_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t ntexels, int C, int Cp)
+{
+    const int G = Cp >> 2;
+    size_t total = ntexels * G;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256)
+    {
+        size_t t = i / G; int k = (int)(i % G) * 4;
+        const float* q = src + t * C + k;
+        float4 v;
+        v.x = __ldg(q);
+        v.y = (k + 1 < C) ? __ldg(q + 1) : 0.f;
+        v.z = (k + 2 < C) ? __ldg(q + 2) : 0.f;
+        v.w = (k + 3 < C) ? __ldg(q + 3) : 0.f;
+        *(float4*)(dst + t * Cp + k) = v;
     }
 }
 
@@ -175,7 +215,7 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_fwd_kernel(const TexParam
             if (p.filter == B200DR_FILTER_NEAREST)
             {
                 int tc = index_nearest(p, uv.x, uv.y, tz);
-                for (int i = 0; i < C; i++) o[i] = texel(p.tex[0], tc, C, i);
+                for (int k = 0; k < p.Cp; k += 4) put4(o, k, C, texel4(p.tex[0], tc, p.Cp, k));
             }
             else
             {
@@ -184,21 +224,22 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_fwd_kernel(const TexParam
                 int4 tc0;
                 float2 uv0 = index_linear(p, uv.x, uv.y, tz, level0, tc0);
                 const float* t0 = p.tex[level0];
+                const int Cp = p.Cp;
                 if (p.filter != B200DR_FILTER_LINEAR_MIPMAP_LINEAR || !(flevel > 0.f))
                 {
-                    for (int i = 0; i < C; i++)
-                        o[i] = bilerp(texel(t0, tc0.x, C, i), texel(t0, tc0.y, C, i), texel(t0, tc0.z, C, i), texel(t0, tc0.w, C, i), uv0);
+                    for (int k = 0; k < Cp; k += 4)
+                        put4(o, k, C, bilerp4(texel4(t0, tc0.x, Cp, k), texel4(t0, tc0.y, Cp, k), texel4(t0, tc0.z, Cp, k), texel4(t0, tc0.w, Cp, k), uv0));
                 }
                 else
                 {
                     int4 tc1;
                     float2 uv1 = index_linear(p, uv.x, uv.y, tz, level1, tc1);
                     const float* t1 = p.tex[level1];
-                    for (int i = 0; i < C; i++)
+                    for (int k = 0; k < Cp; k += 4)
                     {
-                        float a = bilerp(texel(t0, tc0.x, C, i), texel(t0, tc0.y, C, i), texel(t0, tc0.z, C, i), texel(t0, tc0.w, C, i), uv0);
-                        float b = bilerp(texel(t1, tc1.x, C, i), texel(t1, tc1.y, C, i), texel(t1, tc1.z, C, i), texel(t1, tc1.w, C, i), uv1);
-                        o[i] = lerpf(a, b, flevel);
+                        float4 a = bilerp4(texel4(t0, tc0.x, Cp, k), texel4(t0, tc0.y, Cp, k), texel4(t0, tc0.z, Cp, k), texel4(t0, tc0.w, Cp, k), uv0);
+                        float4 b = bilerp4(texel4(t1, tc1.x, Cp, k), texel4(t1, tc1.y, Cp, k), texel4(t1, tc1.z, Cp, k), texel4(t1, tc1.w, Cp, k), uv1);
+                        put4(o, k, C, make_float4(lerpf(a.x, b.x, flevel), lerpf(a.y, b.y, flevel), lerpf(a.z, b.z, flevel), lerpf(a.w, b.w, flevel)));
                     }
                 }
             }
@@ -216,15 +257,30 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_fwd_kernel(const TexParam
 // Backward
 
 // Warp-cooperative texel-gradient accumulation.  Every lane of the warp calls this (inactive lanes pass tc = -1).
-// Lanes that hit the same texel of the same level in consecutive pixels (magnified textures, constant uv such as the
-// background) are summed with shuffles first, so a texel receives one 128-bit vector reduction (REDG.E.ADD.F32x4) per
-// run instead of one atomic per pixel and channel; 32 pixels on one texel cost one reduction, not 32 serialised ones.
-static __device__ __forceinline__ void accum_texel_warp(float* g, int level, int tc, int C, int Cp, float w, const float* dy)
+// reduce == false: every lane issues its own 128-bit vector reduction (REDG.E.ADD.F32x4); measured 150-400 G texel
+//   updates/s on B200 as long as addresses are spread (scripts/atomics_bench.cu).
+// reduce == true : lanes that hit the same texel of the same level in consecutive pixels (strongly magnified textures,
+//   constant uv such as the background) are summed with shuffles first and only the run head issues the reduction;
+//   without this, 32 pixels on one texel are 32 serialised same-address atomics (0.85 clk each, chip-wide).
+// hot: per-CTA one-entry cache per bilinear tap for texels that a whole warp hits at once (constant-uv regions): such
+//   warps add into shared memory and the CTA flushes once, instead of one same-address global reduction per warp.
+#define TEX_HOT_SLOTS 4
+#define TEX_HOT_MAXC  16
+struct HotCache { int key[TEX_HOT_SLOTS]; float val[TEX_HOT_SLOTS][TEX_HOT_MAXC]; };
+
+static __device__ __forceinline__ void accum_texel_warp(float* g, int level, int tc, int C, int Cp, float w, const float* dy, bool reduce,
+                                                        HotCache* hot = 0, int slot = -1)
 {
+    float* q = g + (size_t)(tc >= 0 ? tc : 0) * Cp;
+    if (!reduce)
+    {
+        if (tc < 0) return;
+        for (int k = 0; k < Cp; k += 4)
+            red_add4(q + k, make_float4(w * dy[k], (k + 1 < C) ? w * dy[k + 1] : 0.f, (k + 2 < C) ? w * dy[k + 2] : 0.f, (k + 3 < C) ? w * dy[k + 3] : 0.f));
+        return;
+    }
     int key = (tc >= 0) ? (tc ^ (level << 27)) : -1;
     WarpRuns runs = warp_runs(key);
-    const bool dup = (runs.heads != 0xffffffffu);       // warp-uniform: any two neighbouring lanes on the same texel?
-    float* q = g + (size_t)(tc >= 0 ? tc : 0) * Cp;
     for (int k = 0; k < Cp; k += 4)
     {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -235,25 +291,41 @@ static __device__ __forceinline__ void accum_texel_warp(float* g, int level, int
             v.z = (k + 2 < C) ? w * dy[k + 2] : 0.f;
             v.w = (k + 3 < C) ? w * dy[k + 3] : 0.f;
         }
-        if (dup)
+        v.x = warp_run_sum(v.x, runs);
+        if (k + 1 < C) v.y = warp_run_sum(v.y, runs);
+        if (k + 2 < C) v.z = warp_run_sum(v.z, runs);
+        if (k + 3 < C) v.w = warp_run_sum(v.w, runs);
+        if (runs.is_head && tc >= 0)
         {
-            v.x = warp_run_sum(v.x, runs);
-            if (k + 1 < C) v.y = warp_run_sum(v.y, runs);
-            if (k + 2 < C) v.z = warp_run_sum(v.z, runs);
-            if (k + 3 < C) v.w = warp_run_sum(v.w, runs);
+            bool cached = false;
+            if (hot && runs.heads == 1u)                    // the whole warp sits on this texel
+            {
+                int old = (k == 0) ? atomicCAS(&hot->key[slot], -1, key) : hot->key[slot];
+                if (old == -1 || old == key)
+                {
+                    atomicAdd(&hot->val[slot][k + 0], v.x); atomicAdd(&hot->val[slot][k + 1], v.y);
+                    atomicAdd(&hot->val[slot][k + 2], v.z); atomicAdd(&hot->val[slot][k + 3], v.w);
+                    cached = true;
+                }
+            }
+            if (!cached) red_add4(q + k, v);
         }
-        if (runs.is_head && tc >= 0) red_add4(q + k, v);
     }
 }
 
 __global__ void __launch_bounds__(TEX_THREADS) texture_grad_kernel(const TexParams p)
 {
     extern __shared__ float s_dy[];
+    __shared__ HotCache s_hot;
     const int tid = threadIdx.x;
     const int C = p.C, Cp = p.Cp;
     const size_t hw = (size_t)p.H * p.W;
     const size_t total = hw * p.N;
     const bool trilinear = (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
+    HotCache* hot = (Cp <= TEX_HOT_MAXC) ? &s_hot : 0;
+    if (tid < TEX_HOT_SLOTS) s_hot.key[tid] = -1;
+    if (tid < TEX_HOT_SLOTS * TEX_HOT_MAXC) s_hot.val[tid / TEX_HOT_MAXC][tid % TEX_HOT_MAXC] = 0.f;
+    __syncthreads();
 
     for (int c = blockIdx.x; c < p.chunks; c += gridDim.x)
     {
@@ -304,26 +376,28 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_grad_kernel(const TexPara
         // ---- texel gradients (warp-uniform control flow)
         if (__any_sync(0xffffffffu, act))
         {
+            // few distinct texels in this warp's 32 pixels -> pre-reduce runs; otherwise scatter directly
+            const bool reduce = __popc(warp_runs(act ? (tc0.x ^ (level0 << 27)) : -1).heads) <= 10;
             if (p.filter == B200DR_FILTER_NEAREST)
             {
-                accum_texel_warp(p.gpad[0], 0, tc0.x, C, Cp, 1.f, pDy);
+                accum_texel_warp(p.gpad[0], 0, tc0.x, C, Cp, 1.f, pDy, reduce, hot, 0);
             }
             else
             {
                 float uv011 = uv0.x * uv0.y, uv010 = uv0.x - uv011, uv001 = uv0.y - uv011, uv000 = 1.f - uv0.x - uv001;
                 float* g0 = p.gpad[level0];
-                accum_texel_warp(g0, level0, tc0.x, C, Cp, uv000 * f0, pDy);
-                accum_texel_warp(g0, level0, tc0.y, C, Cp, uv010 * f0, pDy);
-                accum_texel_warp(g0, level0, tc0.z, C, Cp, uv001 * f0, pDy);
-                accum_texel_warp(g0, level0, tc0.w, C, Cp, uv011 * f0, pDy);
+                accum_texel_warp(g0, level0, tc0.x, C, Cp, uv000 * f0, pDy, reduce, hot, 0);
+                accum_texel_warp(g0, level0, tc0.y, C, Cp, uv010 * f0, pDy, reduce, hot, 1);
+                accum_texel_warp(g0, level0, tc0.z, C, Cp, uv001 * f0, pDy, reduce, hot, 2);
+                accum_texel_warp(g0, level0, tc0.w, C, Cp, uv011 * f0, pDy, reduce, hot, 3);
                 if (__any_sync(0xffffffffu, two))
                 {
                     float uv111 = uv1.x * uv1.y, uv110 = uv1.x - uv111, uv101 = uv1.y - uv111, uv100 = 1.f - uv1.x - uv101;
                     float* g1 = p.gpad[level1];
-                    accum_texel_warp(g1, level1, two ? tc1.x : -1, C, Cp, uv100 * flevel, pDy);
-                    accum_texel_warp(g1, level1, two ? tc1.y : -1, C, Cp, uv110 * flevel, pDy);
-                    accum_texel_warp(g1, level1, two ? tc1.z : -1, C, Cp, uv101 * flevel, pDy);
-                    accum_texel_warp(g1, level1, two ? tc1.w : -1, C, Cp, uv111 * flevel, pDy);
+                    accum_texel_warp(g1, level1, two ? tc1.x : -1, C, Cp, uv100 * flevel, pDy, reduce);
+                    accum_texel_warp(g1, level1, two ? tc1.y : -1, C, Cp, uv110 * flevel, pDy, reduce);
+                    accum_texel_warp(g1, level1, two ? tc1.z : -1, C, Cp, uv101 * flevel, pDy, reduce);
+                    accum_texel_warp(g1, level1, two ? tc1.w : -1, C, Cp, uv111 * flevel, pDy, reduce);
                 }
             }
         }
@@ -338,24 +412,32 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_grad_kernel(const TexPara
                 const float* t1 = p.tex[level1];
                 float sclu0 = (float)lvl_w(p, level0), sclv0 = (float)lvl_h(p, level0);
                 float sclu1 = (float)lvl_w(p, level1), sclv1 = (float)lvl_h(p, level1);
-                for (int i = 0; i < C; i++)
+                for (int k = 0; k < Cp; k += 4)
                 {
-                    float dy = pDy[i];
-                    float dy0 = f0 * dy;
-                    float a00 = texel(t0, tc0.x, C, i), a10 = texel(t0, tc0.y, C, i), a01 = texel(t0, tc0.z, C, i), a11 = texel(t0, tc0.w, C, i);
-                    float ad = (a11 + a00 - a10 - a01);
-                    gu += dy0 * ((a10 - a00) + uv0.y * ad) * sclu0;
-                    gv += dy0 * ((a01 - a00) + uv0.x * ad) * sclv0;
-                    if (two)
+                    float4 A00 = texel4(t0, tc0.x, Cp, k), A10 = texel4(t0, tc0.y, Cp, k), A01 = texel4(t0, tc0.z, Cp, k), A11 = texel4(t0, tc0.w, Cp, k);
+                    float4 B00 = make_float4(0.f, 0.f, 0.f, 0.f), B10 = B00, B01 = B00, B11 = B00;
+                    if (two) { B00 = texel4(t1, tc1.x, Cp, k); B10 = texel4(t1, tc1.y, Cp, k); B01 = texel4(t1, tc1.z, Cp, k); B11 = texel4(t1, tc1.w, Cp, k); }
+                    #pragma unroll
+                    for (int j = 0; j < 4; j++)
                     {
-                        float dy1 = flevel * dy;
-                        float b00 = texel(t1, tc1.x, C, i), b10 = texel(t1, tc1.y, C, i), b01 = texel(t1, tc1.z, C, i), b11 = texel(t1, tc1.w, C, i);
-                        float bd = (b11 + b00 - b10 - b01);
-                        gu += dy1 * ((b10 - b00) + uv1.y * bd) * sclu1;
-                        gv += dy1 * ((b01 - b00) + uv1.x * bd) * sclv1;
-                        float a = bilerp(a00, a10, a01, a11, uv0);
-                        float b = bilerp(b00, b10, b01, b11, uv1);
-                        df += (b - a) * dy;
+                        if (k + j >= C) break;
+                        float dy = pDy[k + j];
+                        float dy0 = f0 * dy;
+                        float a00 = (&A00.x)[j], a10 = (&A10.x)[j], a01 = (&A01.x)[j], a11 = (&A11.x)[j];
+                        float ad = (a11 + a00 - a10 - a01);
+                        gu += dy0 * ((a10 - a00) + uv0.y * ad) * sclu0;
+                        gv += dy0 * ((a01 - a00) + uv0.x * ad) * sclv0;
+                        if (two)
+                        {
+                            float dy1 = flevel * dy;
+                            float b00 = (&B00.x)[j], b10 = (&B10.x)[j], b01 = (&B01.x)[j], b11 = (&B11.x)[j];
+                            float bd = (b11 + b00 - b10 - b01);
+                            gu += dy1 * ((b10 - b00) + uv1.y * bd) * sclu1;
+                            gv += dy1 * ((b01 - b00) + uv1.x * bd) * sclv1;
+                            float a = bilerp(a00, a10, a01, a11, uv0);
+                            float b = bilerp(b00, b10, b01, b11, uv1);
+                            df += (b - a) * dy;
+                        }
                     }
                 }
             }
@@ -364,6 +446,19 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_grad_kernel(const TexPara
             if (p.g_uv_da) st_stream_f4((float4*)p.g_uv_da + pidx, make_float4(dw.x * df, dw.y * df, dw.z * df, dw.w * df));
         }
         if (p.staged) __syncthreads();
+    }
+
+    // flush the per-CTA hot-texel cache
+    __syncthreads();
+    if (hot && tid < TEX_HOT_SLOTS * (TEX_HOT_MAXC / 4))
+    {
+        int slot = tid / (TEX_HOT_MAXC / 4), k = (tid % (TEX_HOT_MAXC / 4)) * 4;
+        int key = s_hot.key[slot];
+        if (key != -1 && k < Cp)
+        {
+            int level = (int)((unsigned)key >> 27), tc = key & ((1 << 27) - 1);
+            red_add4(p.gpad[level] + (size_t)tc * Cp + k, make_float4(s_hot.val[slot][k], s_hot.val[slot][k + 1], s_hot.val[slot][k + 2], s_hot.val[slot][k + 3]));
+        }
     }
 }
 
@@ -417,15 +512,18 @@ static int tex_fill(TexParams& p, const char* fn, const float* tex, const float*
     B200DR_CHECK(texD == 1 || texD == N, "%s: minibatch size mismatch between inputs tex, uv", fn);
     B200DR_CHECK(texW <= (1 << TEX_MAX_MIP) && texH <= (1 << TEX_MAX_MIP), "%s: texture size too large", fn);
     B200DR_CHECK(max_level >= 0 && max_level <= TEX_MAX_MIP, "%s: invalid mip level count", fn);
+    B200DR_CHECK((long long)texD * texH * texW < (1ll << 27), "%s: more than 2^27 texels per level are not supported", fn);
     bool mip = (filter == B200DR_FILTER_LINEAR_MIPMAP_NEAREST || filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
     B200DR_CHECK(!mip || uv_da || bias, "%s: mipmapping filter mode requires uv_da and/or mip_level_bias input", fn);
     B200DR_CHECK((((uintptr_t)uv) & 7) == 0, "%s: uv input tensor not aligned to float2", fn);
     B200DR_CHECK(B200DR_ALIGNED16(uv_da), "%s: uv_da input tensor not aligned to float4", fn);
+    B200DR_CHECK(B200DR_ALIGNED16(tex), "%s: padded texture level 0 not aligned to float4", fn);
     p.tex[0] = tex;
     p.mip_max = mip ? max_level : 0;
     for (int i = 1; i <= p.mip_max; i++)
     {
         B200DR_CHECK(mip_ptrs && mip_ptrs[i], "%s: mipmapping filter mode requires mip wrapper or mip stack input", fn);
+        B200DR_CHECK(B200DR_ALIGNED16(mip_ptrs[i]), "%s: padded mip level not aligned to float4", fn);
         p.tex[i] = mip_ptrs[i];
     }
     p.uv = uv; p.uv_da = mip ? uv_da : 0; p.bias = mip ? bias : 0;
@@ -469,6 +567,7 @@ extern "C" int b200dr_texture_construct_mip(const float* tex, float* mip, int te
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     B200DR_CHECK(texD > 0 && texH > 0 && texW > 0 && C > 0, "texture_construct_mip(): tex must have shape[>0, >0, >0, >0]");
+    B200DR_CHECK((C & 3) == 0 && B200DR_ALIGNED16(tex) && B200DR_ALIGNED16(mip), "texture_construct_mip(): expects channel-padded (multiple of 4), 16-byte aligned levels");
     B200DR_CHECK(max_level >= 0 && max_level <= TEX_MAX_MIP, "texture_construct_mip(): invalid max_mip_level");
     for (int L = 1; L <= max_level; L++)
     {
@@ -476,14 +575,30 @@ extern "C" int b200dr_texture_construct_mip(const float* tex, float* mip, int te
         float* out = mip + offsets[L];
         int wi = (texW >> (L - 1)) > 1 ? (texW >> (L - 1)) : 1, hi = (texH >> (L - 1)) > 1 ? (texH >> (L - 1)) : 1;
         int wo = (texW >> L) > 1 ? (texW >> L) : 1, ho = (texH >> L) > 1 ? (texH >> L) : 1;
-        size_t total = (size_t)wo * ho * texD * C;
+        size_t total = (size_t)wo * ho * texD * (C >> 2);
         size_t blocks = (total + 255) / 256;
         size_t cap = (size_t)b200dr_num_sms() * 16;
         if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
         mip_build_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, out, wi, hi, wo, ho, texD, C);
     }
     b200dr_count_launches(max_level - 1);   // max_level kernels, the check below counts one
     B200DR_CHECK_LAUNCH("texture_construct_mip()");
+    return 0;
+}
+
+extern "C" int b200dr_texture_pad(const float* src, float* dst, long long ntexels, int C, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B200DR_CHECK(ntexels > 0 && C > 0, "texture_pad(): empty texture");
+    B200DR_CHECK(B200DR_ALIGNED16(dst), "texture_pad(): destination not aligned to float4");
+    int Cp = (C + 3) & ~3;
+    size_t total = (size_t)ntexels * (Cp >> 2);
+    size_t blocks = (total + 255) / 256;
+    size_t cap = (size_t)b200dr_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    texture_pad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, dst, (size_t)ntexels, C, Cp);
+    B200DR_CHECK_LAUNCH("texture_pad()");
     return 0;
 }
 

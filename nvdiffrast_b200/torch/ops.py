@@ -422,13 +422,23 @@ def interpolate(attr, rast, tri, rast_db=None, diff_attrs=None):
 
 
 class TextureMipWrapper:
-    """Opaque mip stack returned by `texture_construct_mip()` (csrc/torch/torch_types.h:28-35)."""
+    """Opaque mip stack returned by `texture_construct_mip()` (csrc/torch/torch_types.h:28-35).
+    `mip` holds mip levels 1..n packed back to back, each texel padded to a multiple of 4 channels."""
 
     def __init__(self, mip=None, max_mip_level=0, texture_size=(), cube_mode=False):
         self.mip = mip
         self.max_mip_level = max_mip_level
         self.texture_size = tuple(texture_size)
         self.cube_mode = cube_mode
+
+    def level(self, i):
+        """Unpadded view [minibatch, height, width, channels] of mip level i >= 1 (for inspection / tests)."""
+        D, Ht, Wt, C = self.texture_size
+        Cp = (C + 3) & ~3
+        _, offs, level_max = _mip_info("texture_construct_mip", (D, Ht, Wt, Cp), self.max_mip_level)
+        assert 1 <= i <= level_max
+        w, h = max(Wt >> i, 1), max(Ht >> i, 1)
+        return self.mip[offs[i]:offs[i] + D * h * w * Cp].view(D, h, w, Cp)[..., :C]
 
 
 def _mip_info(fn, tex_shape, limit):
@@ -444,25 +454,39 @@ def _mip_info(fn, tex_shape, limit):
     return int(total), offs, int(level_max.value)
 
 
+def _tex_pad(t):
+    """[..., C] -> [..., Cp] with Cp = C rounded up to a multiple of 4 (zero padded); `t` itself when C % 4 == 0."""
+    C = t.shape[-1]
+    Cp = (C + 3) & ~3
+    if Cp == C:
+        return t
+    out = torch.empty(tuple(t.shape[:-1]) + (Cp,), dtype=torch.float32, device=t.device)
+    _lib.call("b200dr_texture_pad", _ptr(t), _ptr(out), t.numel() // C, C, _stream(t.device))
+    return out
+
+
 def _texture_construct_mip(tex, max_mip_level, cube_mode):
     fn = "texture_construct_mip"
-    lib = _lib.load()
+    _lib.load()
     _require(max_mip_level >= -1, fn, "invalid max_mip_level")
     dev = _check_inputs(fn, f32=[("tex", tex)])
     if cube_mode:
         raise NotImplementedError("nvdiffrast_b200: cube map textures are not implemented yet")
     _require(tex.dim() == 4 and min(tex.shape) > 0, fn, "tex must have shape[>0, >0, >0, >0]")
-    total, offs, level_max = _mip_info(fn, tuple(tex.shape), max_mip_level)
+    D, Ht, Wt, C = tex.shape
+    Cp = (C + 3) & ~3
+    total, offs, level_max = _mip_info(fn, (D, Ht, Wt, Cp), max_mip_level)
     with torch.cuda.device(dev):
         mip = torch.empty((total,), dtype=torch.float32, device=dev)
         if level_max > 0:
-            D, Ht, Wt, C = tex.shape
-            _lib.call("b200dr_texture_construct_mip", _ptr(tex), _ptr(mip), Wt, Ht, D, C, offs, level_max, _stream(dev))
+            lvl0 = _tex_pad(tex)
+            _lib.call("b200dr_texture_construct_mip", _ptr(lvl0), _ptr(mip), Wt, Ht, D, Cp, offs, level_max, _stream(dev))
     return TextureMipWrapper(mip, max_mip_level, tuple(tex.shape), cube_mode)
 
 
 def _tex_setup(fn, tex, uv, uv_da, mip_level_bias, mip_wrapper, mip_stack, filter_mode, boundary_mode):
-    """Validation + mip pointer table shared by forward and backward (csrc/torch/torch_texture.cpp:174-330)."""
+    """Validation + padded level pointer table shared by forward and backward (csrc/torch/torch_texture.cpp:174-330).
+    Returns the transient padded tensors too: they must stay referenced until the kernels are enqueued."""
     _require(0 <= filter_mode < 4, fn, "filter_mode unsupported")
     _require(0 <= boundary_mode < 4, fn, "boundary_mode unsupported")
     enable_mip = filter_mode in (2, 3)
@@ -478,12 +502,14 @@ def _tex_setup(fn, tex, uv, uv_da, mip_level_bias, mip_wrapper, mip_stack, filte
     _require(tex.dim() == 4 and min(tex.shape) > 0, fn, "tex must have shape[>0, >0, >0, >0]")
     _require(uv.dim() == 4 and min(uv.shape[:3]) > 0 and uv.shape[3] == 2, fn, "uv must have shape [>0, >0, >0, 2]")
     D, Ht, Wt, C = tex.shape
+    Cp = (C + 3) & ~3
     N, H, W = uv.shape[0], uv.shape[1], uv.shape[2]
     _require(D == 1 or D == N, fn, "minibatch size mismatch between inputs tex, uv")
     _require(Wt <= (1 << _TEX_MAX_MIP_LEVEL) and Ht <= (1 << _TEX_MAX_MIP_LEVEL), fn, "texture size too large")
     level_max = 0
     ptrs = (ctypes.c_void_p * (_TEX_MAX_MIP_LEVEL + 1))()
-    offs = None
+    with torch.cuda.device(dev):
+        keep = [_tex_pad(tex)]
     if enable_mip:
         if has_uv_da:
             _check_inputs(fn, f32=[("tex", tex), ("uv_da", uv_da)])
@@ -507,26 +533,28 @@ def _tex_setup(fn, tex, uv, uv_da, mip_level_bias, mip_wrapper, mip_stack, filte
                 _require(tuple(t.shape) == (D, sh, sw, C), fn, "mip level size mismatch in custom mip stack")
                 if sw == 1 and sh == 1:
                     _require(i == level_max, fn, "mip level size mismatch in mip stack")
-                ptrs[i] = t.data_ptr()
+                with torch.cuda.device(dev):
+                    keep.append(_tex_pad(t.detach()))
+                ptrs[i] = keep[-1].data_ptr()
         else:
-            total, offs, level_max = _mip_info(fn, tuple(tex.shape), mip_wrapper.max_mip_level)
+            total, offs, level_max = _mip_info(fn, (D, Ht, Wt, Cp), mip_wrapper.max_mip_level)
             _require(tuple(tex.shape) == tuple(mip_wrapper.texture_size) and not mip_wrapper.cube_mode, fn, "mip does not match texture size")
             _check_inputs(fn, f32=[("tex", tex), ("mip", mip_wrapper.mip)])
             _require(mip_wrapper.mip.dim() == 1 and mip_wrapper.mip.shape[0] == total, fn, "wrapped mip tensor size mismatch")
             base = mip_wrapper.mip.data_ptr()
             for i in range(1, level_max + 1):
                 ptrs[i] = base + 4 * offs[i]
-    return dev, (N, H, W, D, Ht, Wt, C), enable_mip, has_uv_da, has_bias, level_max, ptrs, offs
+    return dev, (N, H, W, D, Ht, Wt, C), enable_mip, has_uv_da, has_bias, level_max, ptrs, keep
 
 
 def _texture_fwd(tex, uv, uv_da, mip_level_bias, mip_wrapper, mip_stack, filter_mode, boundary_mode):
     fn = "texture_fwd_mip" if filter_mode in (2, 3) else "texture_fwd"
     lib = _lib.load()
-    dev, (N, H, W, D, Ht, Wt, C), enable_mip, has_uv_da, has_bias, level_max, ptrs, _ = \
+    dev, (N, H, W, D, Ht, Wt, C), enable_mip, has_uv_da, has_bias, level_max, ptrs, keep = \
         _tex_setup(fn, tex, uv, uv_da, mip_level_bias, mip_wrapper, mip_stack, filter_mode, boundary_mode)
     with torch.cuda.device(dev):
         out = torch.empty((N, H, W, C), dtype=torch.float32, device=dev)
-        _lib.call("b200dr_texture_fwd", _ptr(tex), ptrs, level_max, _ptr(uv), _ptr(uv_da) if (enable_mip and has_uv_da) else None,
+        _lib.call("b200dr_texture_fwd", _ptr(keep[0]), ptrs, level_max, _ptr(uv), _ptr(uv_da) if (enable_mip and has_uv_da) else None,
                                           _ptr(mip_level_bias) if (enable_mip and has_bias) else None,
                                           N, H, W, D, Ht, Wt, C, filter_mode, boundary_mode, _ptr(out), _stream(dev))
     return out
@@ -536,7 +564,7 @@ def _texture_grad(tex, uv, dy, uv_da, mip_level_bias, mip_wrapper, mip_stack, fi
     """-> (g_tex, g_uv, g_uv_da, g_mip_level_bias, g_mip_stack) (csrc/torch/torch_texture.cpp:421-691)."""
     fn = "texture_grad_linear_mipmap_linear"
     lib = _lib.load()
-    dev, (N, H, W, D, Ht, Wt, C), enable_mip, has_uv_da, has_bias, level_max, ptrs, offs = \
+    dev, (N, H, W, D, Ht, Wt, C), enable_mip, has_uv_da, has_bias, level_max, ptrs, keep = \
         _tex_setup(fn, tex, uv, uv_da, mip_level_bias, mip_wrapper, mip_stack, filter_mode, boundary_mode)
     _check_inputs(fn, f32=[("tex", tex), ("dy", dy)], contiguous=False)
     _require(tuple(dy.shape) == (N, H, W, C), fn, "dy must have shape [minibatch_size, height, width, channels]")
@@ -556,7 +584,7 @@ def _texture_grad(tex, uv, dy, uv_da, mip_level_bias, mip_wrapper, mip_stack, fi
                 g_ptrs[i] = g.data_ptr()
         nbytes = lib.b200dr_texture_grad_scratch_bytes(D, Ht, Wt, C, level_max if enable_mip else 0)
         scratch = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-        _lib.call("b200dr_texture_grad", _ptr(tex), ptrs, level_max, _ptr(uv), _ptr(uv_da) if (enable_mip and has_uv_da) else None,
+        _lib.call("b200dr_texture_grad", _ptr(keep[0]), ptrs, level_max, _ptr(uv), _ptr(uv_da) if (enable_mip and has_uv_da) else None,
                                            _ptr(mip_level_bias) if (enable_mip and has_bias) else None, _ptr(dy),
                                            N, H, W, D, Ht, Wt, C, filter_mode, boundary_mode,
                                            _ptr(g_tex), g_ptrs, int(enable_mip and not has_stack),
