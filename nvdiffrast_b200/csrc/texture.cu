@@ -462,6 +462,242 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_grad_kernel(const TexPara
     }
 }
 
+// ================================================================================================
+// Fast paths: C in {1,2,3,4} (one 128-bit word per texel).  Warp-autonomous like the interpolate kernels: a warp owns
+// groups of 32 consecutive pixels, no block barriers in the loop, one vector access per lane for every per-pixel tensor.
+// ================================================================================================
+
+template <int C>
+static __device__ __forceinline__ void unpack4(float4 v, float (&o)[C])
+{
+    o[0] = v.x;
+    if (C > 1) o[1 % C] = v.y;
+    if (C > 2) o[2 % C] = v.z;
+    if (C > 3) o[3 % C] = v.w;
+}
+
+template <int C>
+__global__ void __launch_bounds__(TEX_THREADS) texture_fwd_fast(const TexParams p)
+{
+    constexpr int SK = (C == 3) ? 3 : 1;
+    __shared__ __align__(16) float s_stage[TEX_THREADS / 32][32 * SK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t hw = (size_t)p.H * p.W;
+    const size_t total = hw * p.N;
+    const size_t groups = (total + 31) >> 5;
+    const size_t wstride = (size_t)gridDim.x * (TEX_THREADS / 32);
+
+    for (size_t g = (size_t)blockIdx.x * (TEX_THREADS / 32) + warp; g < groups; g += wstride)
+    {
+        size_t pidx = g * 32 + lane;
+        bool inb = pidx < total;
+        float o[C];
+        #pragma unroll
+        for (int i = 0; i < C; i++) o[i] = 0.f;
+        if (inb)
+        {
+            float2 uv = ld_stream_f2((const float2*)p.uv + pidx);
+            int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
+            if (p.filter == B200DR_FILTER_NEAREST)
+            {
+                unpack4<C>(texel4(p.tex[0], index_nearest(p, uv.x, uv.y, tz), 4, 0), o);
+            }
+            else
+            {
+                int level0, level1; float flevel; float4 dw;
+                mip_level<false>(p, pidx, level0, level1, flevel, dw);
+                int4 tc0;
+                float2 uv0 = index_linear(p, uv.x, uv.y, tz, level0, tc0);
+                const float* t0 = p.tex[level0];
+                float4 a = bilerp4(texel4(t0, tc0.x, 4, 0), texel4(t0, tc0.y, 4, 0), texel4(t0, tc0.z, 4, 0), texel4(t0, tc0.w, 4, 0), uv0);
+                if (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && flevel > 0.f)
+                {
+                    int4 tc1;
+                    float2 uv1 = index_linear(p, uv.x, uv.y, tz, level1, tc1);
+                    const float* t1 = p.tex[level1];
+                    float4 b = bilerp4(texel4(t1, tc1.x, 4, 0), texel4(t1, tc1.y, 4, 0), texel4(t1, tc1.z, 4, 0), texel4(t1, tc1.w, 4, 0), uv1);
+                    a = make_float4(lerpf(a.x, b.x, flevel), lerpf(a.y, b.y, flevel), lerpf(a.z, b.z, flevel), lerpf(a.w, b.w, flevel));
+                }
+                unpack4<C>(a, o);
+            }
+        }
+        bool full = (g * 32 + 32 <= total);
+        warp_store_aos<C>(p.out + g * 32 * C, o, lane, inb, full, s_stage[warp]);
+    }
+}
+
+// sum v over the whole warp
+static __device__ __forceinline__ float warp_sum(float v)
+{
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// One bilinear tap of the texel-gradient scatter.  uniform: the whole warp sits on this texel with the same weight, `dysum`
+// is the warp-summed incoming gradient; lane 0 adds it to the CTA's hot-texel cache (or to memory if the slot is taken).
+template <int C>
+static __device__ __forceinline__ void scatter_tap(float* g, int level, int tc, float w, const float (&dy)[C], bool uniform,
+                                                   const float (&dysum)[C], HotCache* hot, int slot, int lane)
+{
+    if (tc < 0) return;
+    float* q = g + (size_t)tc * 4;
+    if (!uniform)
+    {
+        red_add4(q, make_float4(w * dy[0], (C > 1) ? w * dy[1 % C] : 0.f, (C > 2) ? w * dy[2 % C] : 0.f, (C > 3) ? w * dy[3 % C] : 0.f));
+        return;
+    }
+    if (lane != 0) return;
+    float4 v = make_float4(w * dysum[0], (C > 1) ? w * dysum[1 % C] : 0.f, (C > 2) ? w * dysum[2 % C] : 0.f, (C > 3) ? w * dysum[3 % C] : 0.f);
+    int key = tc ^ (level << 27);
+    int old = (slot >= 0) ? atomicCAS(&hot->key[slot], -1, key) : 0;
+    if (slot >= 0 && (old == -1 || old == key))
+    {
+        atomicAdd(&hot->val[slot][0], v.x); atomicAdd(&hot->val[slot][1], v.y); atomicAdd(&hot->val[slot][2], v.z); atomicAdd(&hot->val[slot][3], v.w);
+    }
+    else red_add4(q, v);
+}
+
+template <int C>
+__global__ void __launch_bounds__(TEX_THREADS) texture_grad_fast(const TexParams p)
+{
+    constexpr int SK = (C == 3) ? 3 : 1;
+    __shared__ __align__(16) float s_stage[TEX_THREADS / 32][32 * SK];
+    __shared__ HotCache s_hot;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t hw = (size_t)p.H * p.W;
+    const size_t total = hw * p.N;
+    const size_t groups = (total + 31) >> 5;
+    const size_t wstride = (size_t)gridDim.x * (TEX_THREADS / 32);
+    const bool trilinear = (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
+    if (tid < TEX_HOT_SLOTS) s_hot.key[tid] = -1;
+    if (tid < TEX_HOT_SLOTS * TEX_HOT_MAXC) s_hot.val[tid / TEX_HOT_MAXC][tid % TEX_HOT_MAXC] = 0.f;
+    __syncthreads();
+
+    for (size_t g = (size_t)blockIdx.x * (TEX_THREADS / 32) + warp; g < groups; g += wstride)
+    {
+        size_t pidx = g * 32 + lane;
+        bool inb = pidx < total;
+        bool full = (g * 32 + 32 <= total);
+        float dy[C];
+        #pragma unroll
+        for (int i = 0; i < C; i++) dy[i] = 0.f;
+        warp_load_aos<C>(p.dy + g * 32 * C, dy, lane, inb, full, s_stage[warp]);
+        unsigned dmax = 0u;
+        #pragma unroll
+        for (int i = 0; i < C; i++) dmax |= __float_as_uint(dy[i]);
+        bool act = inb && (__uint_as_float(dmax) != 0.f);
+
+        float gu = 0.f, gv = 0.f, df = 0.f;
+        float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (__any_sync(0xffffffffu, act))
+        {
+            int level0 = 0, level1 = 0; float flevel = 0.f;
+            int4 tc0 = make_int4(-1, -1, -1, -1), tc1 = tc0;
+            float2 uv0 = make_float2(0.f, 0.f), uv1 = uv0;
+            bool two = false;
+            float f0 = 1.f;
+            if (act)
+            {
+                int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
+                float2 uv = ld_stream_f2((const float2*)p.uv + pidx);
+                if (p.filter == B200DR_FILTER_NEAREST) tc0.x = index_nearest(p, uv.x, uv.y, tz);
+                else
+                {
+                    mip_level<true>(p, pidx, level0, level1, flevel, dw);
+                    uv0 = index_linear(p, uv.x, uv.y, tz, level0, tc0);
+                    two = trilinear && (flevel > 0.f);
+                    f0 = trilinear ? (1.f - flevel) : 1.f;
+                    if (two) uv1 = index_linear(p, uv.x, uv.y, tz, level1, tc1);
+                }
+            }
+            // Whole warp on one texel quad with identical weights (constant uv, e.g. background)?  Then reduce dy once.
+            int key0 = act ? (tc0.x ^ (level0 << 27)) : -1;
+            bool uniform = __all_sync(0xffffffffu, act && !two && key0 == __shfl_sync(0xffffffffu, key0, 0) &&
+                                      __float_as_int(uv0.x) == __shfl_sync(0xffffffffu, __float_as_int(uv0.x), 0) &&
+                                      __float_as_int(uv0.y) == __shfl_sync(0xffffffffu, __float_as_int(uv0.y), 0));
+            float dysum[C];
+            #pragma unroll
+            for (int i = 0; i < C; i++) dysum[i] = uniform ? warp_sum(dy[i]) : 0.f;
+
+            if (p.filter == B200DR_FILTER_NEAREST)
+            {
+                scatter_tap<C>(p.gpad[0], 0, tc0.x, 1.f, dy, uniform, dysum, &s_hot, 0, lane);
+            }
+            else
+            {
+                float uv011 = uv0.x * uv0.y, uv010 = uv0.x - uv011, uv001 = uv0.y - uv011, uv000 = 1.f - uv0.x - uv001;
+                float* g0 = p.gpad[level0];
+                scatter_tap<C>(g0, level0, tc0.x, uv000 * f0, dy, uniform, dysum, &s_hot, 0, lane);
+                scatter_tap<C>(g0, level0, tc0.y, uv010 * f0, dy, uniform, dysum, &s_hot, 1, lane);
+                scatter_tap<C>(g0, level0, tc0.z, uv001 * f0, dy, uniform, dysum, &s_hot, 2, lane);
+                scatter_tap<C>(g0, level0, tc0.w, uv011 * f0, dy, uniform, dysum, &s_hot, 3, lane);
+                if (two)
+                {
+                    float uv111 = uv1.x * uv1.y, uv110 = uv1.x - uv111, uv101 = uv1.y - uv111, uv100 = 1.f - uv1.x - uv101;
+                    float* g1 = p.gpad[level1];
+                    scatter_tap<C>(g1, level1, tc1.x, uv100 * flevel, dy, false, dysum, &s_hot, -1, lane);
+                    scatter_tap<C>(g1, level1, tc1.y, uv110 * flevel, dy, false, dysum, &s_hot, -1, lane);
+                    scatter_tap<C>(g1, level1, tc1.z, uv101 * flevel, dy, false, dysum, &s_hot, -1, lane);
+                    scatter_tap<C>(g1, level1, tc1.w, uv111 * flevel, dy, false, dysum, &s_hot, -1, lane);
+                }
+                if (act)
+                {
+                    const float* t0 = p.tex[level0];
+                    float sclu0 = (float)lvl_w(p, level0), sclv0 = (float)lvl_h(p, level0);
+                    float a00[C], a10[C], a01[C], a11[C];
+                    unpack4<C>(texel4(t0, tc0.x, 4, 0), a00); unpack4<C>(texel4(t0, tc0.y, 4, 0), a10);
+                    unpack4<C>(texel4(t0, tc0.z, 4, 0), a01); unpack4<C>(texel4(t0, tc0.w, 4, 0), a11);
+                    #pragma unroll
+                    for (int i = 0; i < C; i++)
+                    {
+                        float dy0 = f0 * dy[i];
+                        float ad = (a11[i] + a00[i] - a10[i] - a01[i]);
+                        gu += dy0 * ((a10[i] - a00[i]) + uv0.y * ad) * sclu0;
+                        gv += dy0 * ((a01[i] - a00[i]) + uv0.x * ad) * sclv0;
+                    }
+                    if (two)
+                    {
+                        const float* t1 = p.tex[level1];
+                        float sclu1 = (float)lvl_w(p, level1), sclv1 = (float)lvl_h(p, level1);
+                        float b00[C], b10[C], b01[C], b11[C];
+                        unpack4<C>(texel4(t1, tc1.x, 4, 0), b00); unpack4<C>(texel4(t1, tc1.y, 4, 0), b10);
+                        unpack4<C>(texel4(t1, tc1.z, 4, 0), b01); unpack4<C>(texel4(t1, tc1.w, 4, 0), b11);
+                        #pragma unroll
+                        for (int i = 0; i < C; i++)
+                        {
+                            float dy1 = flevel * dy[i];
+                            float bd = (b11[i] + b00[i] - b10[i] - b01[i]);
+                            gu += dy1 * ((b10[i] - b00[i]) + uv1.y * bd) * sclu1;
+                            gv += dy1 * ((b01[i] - b00[i]) + uv1.x * bd) * sclv1;
+                            float a = bilerp(a00[i], a10[i], a01[i], a11[i], uv0);
+                            float b = bilerp(b00[i], b10[i], b01[i], b11[i], uv1);
+                            df += (b - a) * dy[i];
+                        }
+                    }
+                }
+            }
+        }
+        if (inb)
+        {
+            if (p.g_uv) st_stream_f2((float2*)p.g_uv + pidx, make_float2(gu, gv));
+            if (p.g_bias) st_stream_f(p.g_bias + pidx, df);
+            if (p.g_uv_da) st_stream_f4((float4*)p.g_uv_da + pidx, make_float4(dw.x * df, dw.y * df, dw.z * df, dw.w * df));
+        }
+    }
+
+    __syncthreads();
+    if (tid < TEX_HOT_SLOTS)
+    {
+        int key = s_hot.key[tid];
+        if (key != -1)
+        {
+            int level = (int)((unsigned)key >> 27), tc = key & ((1 << 27) - 1);
+            red_add4(p.gpad[level] + (size_t)tc * 4, make_float4(s_hot.val[tid][0], s_hot.val[tid][1], s_hot.val[tid][2], s_hot.val[tid][3]));
+        }
+    }
+}
+
 // Resolve: g_out[texel][c] = pad[0][texel][c] (+ sum over levels of weight * pad[L][parent texel][c] when pulling mips),
 // written in the caller's C-channel layout.  Pull weights as in MipGradKernel (texture_kernel.cu:843-900).
 struct ResolveParams
@@ -611,6 +847,21 @@ extern "C" int b200dr_texture_fwd(const float* tex, const float* const* mip_ptrs
     TexParams p = {};
     if (tex_fill(p, "texture_fwd()", tex, mip_ptrs, max_level, uv, uv_da, mip_level_bias, N, H, W, texD, texH, texW, C, filter_mode, boundary_mode)) return 1;
     p.out = out;
+    if (C <= 4 && B200DR_ALIGNED16(out))
+    {
+        size_t groups = ((size_t)N * H * W + 31) / 32;
+        size_t blocks = (groups + (TEX_THREADS / 32) - 1) / (TEX_THREADS / 32);
+        size_t bcap = (size_t)b200dr_num_sms() * 12;
+        if (blocks > bcap) blocks = bcap;
+        switch (C) {
+        case 1: texture_fwd_fast<1><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
+        case 2: texture_fwd_fast<2><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
+        case 3: texture_fwd_fast<3><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
+        case 4: texture_fwd_fast<4><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
+        }
+        B200DR_CHECK_LAUNCH("texture_fwd()");
+        return 0;
+    }
     size_t smem = (size_t)TEX_THREADS * C * sizeof(float);
     p.staged = smem <= 96 * 1024;
     if (!p.staged) smem = 0;
@@ -667,14 +918,30 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
         }
     }
 
-    size_t smem = (size_t)TEX_THREADS * C * sizeof(float);
-    p.staged = smem <= 96 * 1024;
-    if (!p.staged) smem = 0;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(texture_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    int grid = p.chunks;
-    int cap = b200dr_num_sms() * 16;
-    if (grid > cap) grid = cap;
-    texture_grad_kernel<<<grid, TEX_THREADS, smem, stream>>>(p);
+    if (C <= 4 && B200DR_ALIGNED16(dy))
+    {
+        size_t groups = ((size_t)N * H * W + 31) / 32;
+        size_t blocks = (groups + (TEX_THREADS / 32) - 1) / (TEX_THREADS / 32);
+        size_t bcap = (size_t)b200dr_num_sms() * 8;
+        if (blocks > bcap) blocks = bcap;
+        switch (C) {
+        case 1: texture_grad_fast<1><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
+        case 2: texture_grad_fast<2><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
+        case 3: texture_grad_fast<3><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
+        case 4: texture_grad_fast<4><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
+        }
+    }
+    else
+    {
+        size_t smem = (size_t)TEX_THREADS * C * sizeof(float);
+        p.staged = smem <= 96 * 1024;
+        if (!p.staged) smem = 0;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(texture_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        int grid = p.chunks;
+        int cap = b200dr_num_sms() * 16;
+        if (grid > cap) grid = cap;
+        texture_grad_kernel<<<grid, TEX_THREADS, smem, stream>>>(p);
+    }
     B200DR_CHECK_LAUNCH("texture_grad()");
 
     // resolve into the caller's layout
