@@ -613,9 +613,12 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_grad_fast(const TexParams
             }
             // Whole warp on one texel quad with identical weights (constant uv, e.g. background)?  Then reduce dy once.
             int key0 = act ? (tc0.x ^ (level0 << 27)) : -1;
-            bool uniform = __all_sync(0xffffffffu, act && !two && key0 == __shfl_sync(0xffffffffu, key0, 0) &&
-                                      __float_as_int(uv0.x) == __shfl_sync(0xffffffffu, __float_as_int(uv0.x), 0) &&
-                                      __float_as_int(uv0.y) == __shfl_sync(0xffffffffu, __float_as_int(uv0.y), 0));
+            // (shuffles are evaluated by every lane BEFORE the boolean expression: no short-circuit around warp collectives)
+            int k0 = __shfl_sync(0xffffffffu, key0, 0);
+            int u0 = __shfl_sync(0xffffffffu, __float_as_int(uv0.x), 0);
+            int v0 = __shfl_sync(0xffffffffu, __float_as_int(uv0.y), 0);
+            bool same = act && !two && (key0 == k0) && (__float_as_int(uv0.x) == u0) && (__float_as_int(uv0.y) == v0);
+            bool uniform = __all_sync(0xffffffffu, same);
             float dysum[C];
             #pragma unroll
             for (int i = 0; i < C; i++) dysum[i] = uniform ? warp_sum(dy[i]) : 0.f;
