@@ -309,7 +309,8 @@ static __device__ __forceinline__ Edge make_edge(int ax, int ay, int bx, int by,
 
 #define BIN_LOG2   6
 #define BIN_SIZE   64
-#define BIN_LIST   384          // per-bin triangle list capacity in shared memory; longer lists are processed in rounds
+#define BIN_LIST   256          // triangles set up in shared memory at a time (longer per-bin lists are processed in chunks)
+#define BIN_IDX    2048         // records scanned per segment = capacity of the per-bin index list
 #define BIN_THREADS 256
 
 struct __align__(16) BinTri     // 64 bytes, broadcast-read by every thread of the CTA
@@ -398,7 +399,8 @@ static __device__ __forceinline__ int s16hi(uint32_t v) { return (int)v >> 16; }
 template <bool PEEL_IN, bool DEPTH_OUT>
 __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastParams p)
 {
-    __shared__ BinTri   s_tri[BIN_LIST];            // 24 KB
+    __shared__ BinTri   s_tri[BIN_LIST];            // 16 KB
+    __shared__ int      s_idx[BIN_IDX];             //  8 KB
     __shared__ uint32_t s_ids[BIN_SIZE * BIN_SIZE]; // 16 KB
     __shared__ int      s_count;
 
@@ -439,20 +441,34 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
     const uint2* bboxes = p.bbox + (size_t)n * p.cap;
     const uint4* recs = p.rec + (size_t)n * p.cap * 2;
 
-    if (tid == 0) s_count = 0;
-    __syncthreads();
-
     bool any = false;
-    for (int base = 0; base < total; base += BIN_THREADS)
+    // Records are scanned in segments of BIN_IDX records (the index list cannot overflow); within a segment the scan loop
+    // has no barrier: every thread tests bounding boxes and appends the indices of this bin's triangles to s_idx.
+    for (int seg = 0; seg < total; seg += BIN_IDX)
     {
-        // ---- scan: one record per thread, append the bin's triangles (with bin-relative edge setup) to s_tri
-        int i = base + tid;
-        if (i < total)
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        const int seg_end = min(seg + BIN_IDX, total);
+        for (int i = seg + tid; i < seg_end; i += BIN_THREADS)
         {
             uint2 bb = __ldg(bboxes + i);
             int x0 = (int)(bb.x & 0xFFFFu), x1 = (int)(bb.x >> 16), y0 = (int)(bb.y & 0xFFFFu), y1 = (int)(bb.y >> 16);
             if (x0 <= binX1 && x1 >= binX0 && y0 <= binY1 && y1 >= binY0 && x0 <= x1)
+                s_idx[atomicAdd(&s_count, 1)] = i;
+        }
+        __syncthreads();
+        const int nidx = s_count;
+        if (nidx > 0) any = true;
+
+        // ---- rasterize this bin's triangles, BIN_LIST at a time
+        for (int lb = 0; lb < nidx; lb += BIN_LIST)
+        {
+            const int cnt = min(BIN_LIST, nidx - lb);
+            for (int j = tid; j < cnt; j += BIN_THREADS)        // bin-relative edge / depth setup, one triangle per thread
             {
+                int i = s_idx[lb + j];
+                uint2 bb = __ldg(bboxes + i);
+                int x0 = (int)(bb.x & 0xFFFFu), x1 = (int)(bb.x >> 16), y0 = (int)(bb.y & 0xFFFFu), y1 = (int)(bb.y >> 16);
                 uint4 ra = __ldg(recs + i * 2), rb = __ldg(recs + i * 2 + 1);
                 int ax = s16lo(ra.x), ay = s16hi(ra.x), bx = s16lo(ra.y), by = s16hi(ra.y), cx = s16lo(ra.z), cy = s16hi(ra.z);
                 Edge e0 = make_edge(ax, ay, bx, by, binX0, binY0, p.W, p.H);
@@ -468,59 +484,49 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
                 t.box = (uint32_t)(max(x0, binX0) - binX0) | ((uint32_t)(min(x1, binX1) - binX0) << 8) |
                         ((uint32_t)(max(y0, binY0) - binY0) << 16) | ((uint32_t)(min(y1, binY1) - binY0) << 24);
                 t.pad0 = 0; t.pad1 = 0;
-                int slot = atomicAdd(&s_count, 1);
-                s_tri[slot] = t;
+                s_tri[j] = t;
             }
-        }
-        // ---- rasterize the list when it may overflow next round, or at the end
-        bool last = (base + BIN_THREADS >= total);
-        __syncthreads();
-        int cnt = s_count;
-        __syncthreads();                                        // everyone has read cnt before the next round appends
-        if (!last && cnt <= BIN_LIST - BIN_THREADS) continue;   // uniform decision
-
-        if (cnt > 0) any = true;
-        for (int k = 0; k < cnt; k++)
-        {
-            uint32_t box = s_tri[k].box;
-            int x0 = (int)(box & 0xFF), x1 = (int)((box >> 8) & 0xFF), y0 = (int)((box >> 16) & 0xFF), y1 = (int)(box >> 24);
-            if (tx > x1 || tx + 3 < x0 || ty > y1 || ty + 3 < y0) continue;
-            const int4* q = (const int4*)&s_tri[k];
-            int4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
-            int e0sx = q0.y, e0sy = q0.z, e1sx = q1.x, e1sy = q1.y, e2sx = q1.w, e2sy = q2.x;
-            int e0 = q0.x + e0sx * tx + e0sy * ty;
-            int e1 = q0.w + e1sx * tx + e1sy * ty;
-            int e2 = q1.z + e2sx * tx + e2sy * ty;
-            // trivial reject of the 4x4 block: the largest value of an edge function over the block is still negative
-            if ((e0 + 3 * max(e0sx, 0) + 3 * max(e0sy, 0)) < 0) continue;
-            if ((e1 + 3 * max(e1sx, 0) + 3 * max(e1sy, 0)) < 0) continue;
-            if ((e2 + 3 * max(e2sx, 0) + 3 * max(e2sy, 0)) < 0) continue;
-            uint32_t zx = (uint32_t)q2.z, zy = (uint32_t)q2.w;
-            uint32_t zr = (uint32_t)q2.y + zx * (uint32_t)tx + zy * (uint32_t)ty;
-            uint32_t id = (uint32_t)q3.x;
-            #pragma unroll
-            for (int j = 0; j < 4; j++)
+            __syncthreads();
+            for (int k = 0; k < cnt; k++)
             {
-                int f0 = e0, f1 = e1, f2 = e2;
-                uint32_t z = zr;
+                uint32_t box = s_tri[k].box;
+                int x0 = (int)(box & 0xFF), x1 = (int)((box >> 8) & 0xFF), y0 = (int)((box >> 16) & 0xFF), y1 = (int)(box >> 24);
+                if (tx > x1 || tx + 3 < x0 || ty > y1 || ty + 3 < y0) continue;
+                const int4* q = (const int4*)&s_tri[k];
+                int4 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+                int e0sx = q0.y, e0sy = q0.z, e1sx = q1.x, e1sy = q1.y, e2sx = q1.w, e2sy = q2.x;
+                int e0 = q0.x + e0sx * tx + e0sy * ty;
+                int e1 = q0.w + e1sx * tx + e1sy * ty;
+                int e2 = q1.z + e2sx * tx + e2sy * ty;
+                // trivial reject of the 4x4 block: the largest value of an edge function over the block is still negative
+                if ((e0 + 3 * max(e0sx, 0) + 3 * max(e0sy, 0)) < 0) continue;
+                if ((e1 + 3 * max(e1sx, 0) + 3 * max(e1sy, 0)) < 0) continue;
+                if ((e2 + 3 * max(e2sx, 0) + 3 * max(e2sy, 0)) < 0) continue;
+                uint32_t zx = (uint32_t)q2.z, zy = (uint32_t)q2.w;
+                uint32_t zr = (uint32_t)q2.y + zx * (uint32_t)tx + zy * (uint32_t)ty;
+                uint32_t id = (uint32_t)q3.x;
                 #pragma unroll
-                for (int i = 0; i < 4; i++)
+                for (int j = 0; j < 4; j++)
                 {
-                    if ((f0 | f1 | f2) >= 0)
+                    int f0 = e0, f1 = e1, f2 = e2;
+                    uint32_t z = zr;
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++)
                     {
-                        const int s = j * 4 + i;
-                        bool pass = (z < bestD[s]) || (z == bestD[s] && id > bestI[s]);
-                        if (PEEL_IN) pass = pass && (z > peelD[s]);
-                        if (pass) { bestD[s] = z; bestI[s] = id; }
+                        if ((f0 | f1 | f2) >= 0)
+                        {
+                            const int sidx = j * 4 + i;
+                            bool pass = (z < bestD[sidx]) || (z == bestD[sidx] && id > bestI[sidx]);
+                            if (PEEL_IN) pass = pass && (z > peelD[sidx]);
+                            if (pass) { bestD[sidx] = z; bestI[sidx] = id; }
+                        }
+                        f0 += e0sx; f1 += e1sx; f2 += e2sx; z += zx;
                     }
-                    f0 += e0sx; f1 += e1sx; f2 += e2sx; z += zx;
+                    e0 += e0sy; e1 += e1sy; e2 += e2sy; zr += zy;
                 }
-                e0 += e0sy; e1 += e1sy; e2 += e2sy; zr += zy;
             }
+            __syncthreads();                                    // s_tri is rebuilt by the next chunk
         }
-        __syncthreads();                                        // list consumed
-        if (tid == 0) s_count = 0;
-        __syncthreads();
     }
 
     // Note: a fragment whose depth equals DR_DEPTH_MAX with id >= 1 wins over the cleared pixel (equal depth passes),
@@ -744,13 +750,93 @@ struct RastGradParams
     float xs, xo, ys, yo;
 };
 
+// Gradient of one pixel w.r.t. the clip-space positions of its triangle (csrc/common/rasterize.cu:160-267).
 template <bool ENABLE_DB>
-__global__ void __launch_bounds__(256) raster_grad_kernel(const RastGradParams p)
+static __device__ __forceinline__ void raster_grad_pixel(const RastGradParams& p, int n, int px, int py, int vi0, int vi1, int vi2,
+                                                         float2 dy, float4 ddb, bool has_ddb, float (&g)[9])
+{
+    const float4* vb = (const float4*)p.pos + (p.instance_mode ? (size_t)n * p.V : 0);
+    float4 p0 = __ldg(vb + vi0), p1 = __ldg(vb + vi1), p2 = __ldg(vb + vi2);
+
+    float fx = p.xs * (float)px + p.xo;
+    float fy = p.ys * (float)py + p.yo;
+    float p0x = p0.x - fx * p0.w, p0y = p0.y - fy * p0.w;
+    float p1x = p1.x - fx * p1.w, p1y = p1.y - fy * p1.w;
+    float p2x = p2.x - fx * p2.w, p2y = p2.y - fy * p2.w;
+    float a0 = p1x * p2y - p1y * p2x;
+    float a1 = p2x * p0y - p2y * p0x;
+    float a2 = p0x * p1y - p0y * p1x;
+
+    float at = a0 + a1 + a2;
+    float ep = copysignf(1e-6f, at);
+    float iw = 1.f / (at + ep);
+    float b0 = a0 * iw, b1 = a1 * iw;
+
+    float gb0 = dy.x * iw, gb1 = dy.y * iw;
+    float gbb = gb0 * b0 + gb1 * b1;
+    float gp0x = gbb * (p2y - p1y) - gb1 * p2y;
+    float gp1x = gbb * (p0y - p2y) + gb0 * p2y;
+    float gp2x = gbb * (p1y - p0y) - gb0 * p1y + gb1 * p0y;
+    float gp0y = gbb * (p1x - p2x) + gb1 * p2x;
+    float gp1y = gbb * (p2x - p0x) - gb0 * p2x;
+    float gp2y = gbb * (p0x - p1x) + gb0 * p1x - gb1 * p0x;
+    float gp0w = -fx * gp0x - fy * gp0y;
+    float gp1w = -fx * gp1x - fy * gp1y;
+    float gp2w = -fx * gp2x - fy * gp2y;
+
+    if (ENABLE_DB && has_ddb)
+    {
+        float dfxdX = p.xs * iw, dfydY = p.ys * iw;
+        ddb.x *= dfxdX; ddb.y *= dfydY; ddb.z *= dfxdX; ddb.w *= dfydY;
+
+        float da0dX = p1.y * p2.w - p2.y * p1.w, da1dX = p2.y * p0.w - p0.y * p2.w, da2dX = p0.y * p1.w - p1.y * p0.w;
+        float da0dY = p2.x * p1.w - p1.x * p2.w, da1dY = p0.x * p2.w - p2.x * p0.w, da2dY = p1.x * p0.w - p0.x * p1.w;
+        float datdX = da0dX + da1dX + da2dX, datdY = da0dY + da1dY + da2dY;
+
+        float x01 = p0.x - p1.x, x12 = p1.x - p2.x, x20 = p2.x - p0.x;
+        float y01 = p0.y - p1.y, y12 = p1.y - p2.y, y20 = p2.y - p0.y;
+        float w01 = p0.w - p1.w, w12 = p1.w - p2.w, w20 = p2.w - p0.w;
+
+        float a0p1 = fy * p2.x - fx * p2.y, a0p2 = fx * p1.y - fy * p1.x;
+        float a1p0 = fx * p2.y - fy * p2.x, a1p2 = fy * p0.x - fx * p0.y;
+
+        float wdudX = 2.f * b0 * datdX - da0dX, wdudY = 2.f * b0 * datdY - da0dY;
+        float wdvdX = 2.f * b1 * datdX - da1dX, wdvdY = 2.f * b1 * datdY - da1dY;
+
+        float c0  = iw * (ddb.x * wdudX + ddb.y * wdudY + ddb.z * wdvdX + ddb.w * wdvdY);
+        float cx  = c0 * fx - ddb.x * b0 - ddb.z * b1;
+        float cy  = c0 * fy - ddb.y * b0 - ddb.w * b1;
+        float cxy = iw * (ddb.x * datdX + ddb.y * datdY);
+        float czw = iw * (ddb.z * datdX + ddb.w * datdY);
+
+        gp0x += c0 * y12 - cy * w12              + czw * p2y                                               + ddb.w * p2.w;
+        gp1x += c0 * y20 - cy * w20 - cxy * p2y                              - ddb.y * p2.w;
+        gp2x += c0 * y01 - cy * w01 + cxy * p1y  - czw * p0y                 + ddb.y * p1.w                - ddb.w * p0.w;
+        gp0y += cx * w12 - c0 * x12              - czw * p2x                                - ddb.z * p2.w;
+        gp1y += cx * w20 - c0 * x20 + cxy * p2x               + ddb.x * p2.w;
+        gp2y += cx * w01 - c0 * x01 - cxy * p1x  + czw * p0x  - ddb.x * p1.w                + ddb.z * p0.w;
+        gp0w += cy * x12 - cx * y12              - czw * a1p0                               + ddb.z * p2.y - ddb.w * p2.x;
+        gp1w += cy * x20 - cx * y20 - cxy * a0p1              - ddb.x * p2.y + ddb.y * p2.x;
+        gp2w += cy * x01 - cx * y01 - cxy * a0p2 - czw * a1p2 + ddb.x * p1.y - ddb.y * p1.x - ddb.z * p0.y + ddb.w * p0.x;
+    }
+    g[0] = gp0x; g[1] = gp0y; g[2] = gp0w;
+    g[3] = gp1x; g[4] = gp1y; g[5] = gp1w;
+    g[6] = gp2x; g[7] = gp2y; g[8] = gp2w;
+}
+
+#define RG_UNROLL 2
+
+// Warp-autonomous: a warp owns groups of 32 consecutive pixels of image blockIdx.y, two groups in flight.
+template <bool ENABLE_DB>
+__global__ void __launch_bounds__(256, 4) raster_grad_kernel(const RastGradParams p)
 {
     extern __shared__ float s_acc[];
     const int n = blockIdx.y;
-    const int tid = threadIdx.x;
-    const size_t hw = (size_t)p.H * p.W;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int hw = p.H * p.W;
+    const int groups = (hw + 31) >> 5;
+    const int wstride = gridDim.x * 8;
+    const size_t img = (size_t)n * hw;
     float* gbase = p.grad + (p.instance_mode ? (size_t)n * p.V * 4 : 0);
     float* acc = p.use_smem ? s_acc : gbase;
     if (p.use_smem)
@@ -759,119 +845,59 @@ __global__ void __launch_bounds__(256) raster_grad_kernel(const RastGradParams p
         __syncthreads();
     }
 
-    for (int c = blockIdx.x; c < p.chunks; c += gridDim.x)
+    for (int g0 = blockIdx.x * 8 + warp; g0 < groups; g0 += RG_UNROLL * wstride)
     {
-        size_t r = (size_t)c * 256 + tid;
-        bool inb = r < hw;
-        size_t pidx = (size_t)n * hw + (inb ? r : 0);
-
-        int triIdx = -1;
-        float2 dy = make_float2(0.f, 0.f);
-        float4 ddb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (inb)
-        {
-            float4 ro = ld_stream_f4((const float4*)p.rast + pidx);
-            dy = ld_stream_f2((const float2*)p.dy + pidx * 2);
-            if (ENABLE_DB) ddb = ld_stream_f4((const float4*)p.ddb + pidx);
-            triIdx = float_to_triidx(ro.w) - 1;
-            if (triIdx < 0 || triIdx >= p.T) triIdx = -1;
-        }
-        int grad_all_dy = __float_as_int(dy.x) | __float_as_int(dy.y);
-        int grad_all_ddb = ENABLE_DB ? (__float_as_int(ddb.x) | __float_as_int(ddb.y) | __float_as_int(ddb.z) | __float_as_int(ddb.w)) : 0;
-        if (((grad_all_dy | grad_all_ddb) << 1) == 0) triIdx = -1;     // all incoming gradients are +-0
-
-        int vi0 = 0, vi1 = 0, vi2 = 0;
-        if (triIdx >= 0)
-        {
-            vi0 = __ldg(p.tri + triIdx * 3 + 0); vi1 = __ldg(p.tri + triIdx * 3 + 1); vi2 = __ldg(p.tri + triIdx * 3 + 2);
-            if (vi0 < 0 || vi0 >= p.V || vi1 < 0 || vi1 >= p.V || vi2 < 0 || vi2 >= p.V) triIdx = -1;
-        }
-        if (__all_sync(0xffffffffu, triIdx < 0)) continue;
-
-        float g[9];
+        float4 ro[RG_UNROLL], ddb[RG_UNROLL]; float2 dy[RG_UNROLL]; bool inb[RG_UNROLL];
         #pragma unroll
-        for (int i = 0; i < 9; i++) g[i] = 0.f;
-        if (triIdx >= 0)
+        for (int u = 0; u < RG_UNROLL; u++)
         {
-            int py = (int)(r / p.W), px = (int)(r - (size_t)py * p.W);
-            const float4* vb = (const float4*)p.pos + (p.instance_mode ? (size_t)n * p.V : 0);
-            float4 p0 = __ldg(vb + vi0), p1 = __ldg(vb + vi1), p2 = __ldg(vb + vi2);
-
-            float fx = p.xs * (float)px + p.xo;
-            float fy = p.ys * (float)py + p.yo;
-            float p0x = p0.x - fx * p0.w, p0y = p0.y - fy * p0.w;
-            float p1x = p1.x - fx * p1.w, p1y = p1.y - fy * p1.w;
-            float p2x = p2.x - fx * p2.w, p2y = p2.y - fy * p2.w;
-            float a0 = p1x * p2y - p1y * p2x;
-            float a1 = p2x * p0y - p2y * p0x;
-            float a2 = p0x * p1y - p0y * p1x;
-
-            float at = a0 + a1 + a2;
-            float ep = copysignf(1e-6f, at);
-            float iw = 1.f / (at + ep);
-            float b0 = a0 * iw, b1 = a1 * iw;
-
-            float gb0 = dy.x * iw, gb1 = dy.y * iw;
-            float gbb = gb0 * b0 + gb1 * b1;
-            float gp0x = gbb * (p2y - p1y) - gb1 * p2y;
-            float gp1x = gbb * (p0y - p2y) + gb0 * p2y;
-            float gp2x = gbb * (p1y - p0y) - gb0 * p1y + gb1 * p0y;
-            float gp0y = gbb * (p1x - p2x) + gb1 * p2x;
-            float gp1y = gbb * (p2x - p0x) - gb0 * p2x;
-            float gp2y = gbb * (p0x - p1x) + gb0 * p1x - gb1 * p0x;
-            float gp0w = -fx * gp0x - fy * gp0y;
-            float gp1w = -fx * gp1x - fy * gp1y;
-            float gp2w = -fx * gp2x - fy * gp2y;
-
-            if (ENABLE_DB && ((grad_all_ddb) << 1) != 0)
+            int r = (g0 + u * wstride) * 32 + lane;
+            inb[u] = (g0 + u * wstride < groups) && (r < hw);
+            ro[u] = make_float4(0.f, 0.f, 0.f, 0.f); ddb[u] = ro[u]; dy[u] = make_float2(0.f, 0.f);
+            if (inb[u])
             {
-                float dfxdX = p.xs * iw, dfydY = p.ys * iw;
-                ddb.x *= dfxdX; ddb.y *= dfydY; ddb.z *= dfxdX; ddb.w *= dfydY;
-
-                float da0dX = p1.y * p2.w - p2.y * p1.w, da1dX = p2.y * p0.w - p0.y * p2.w, da2dX = p0.y * p1.w - p1.y * p0.w;
-                float da0dY = p2.x * p1.w - p1.x * p2.w, da1dY = p0.x * p2.w - p2.x * p0.w, da2dY = p1.x * p0.w - p0.x * p1.w;
-                float datdX = da0dX + da1dX + da2dX, datdY = da0dY + da1dY + da2dY;
-
-                float x01 = p0.x - p1.x, x12 = p1.x - p2.x, x20 = p2.x - p0.x;
-                float y01 = p0.y - p1.y, y12 = p1.y - p2.y, y20 = p2.y - p0.y;
-                float w01 = p0.w - p1.w, w12 = p1.w - p2.w, w20 = p2.w - p0.w;
-
-                float a0p1 = fy * p2.x - fx * p2.y, a0p2 = fx * p1.y - fy * p1.x;
-                float a1p0 = fx * p2.y - fy * p2.x, a1p2 = fy * p0.x - fx * p0.y;
-
-                float wdudX = 2.f * b0 * datdX - da0dX, wdudY = 2.f * b0 * datdY - da0dY;
-                float wdvdX = 2.f * b1 * datdX - da1dX, wdvdY = 2.f * b1 * datdY - da1dY;
-
-                float c0  = iw * (ddb.x * wdudX + ddb.y * wdudY + ddb.z * wdvdX + ddb.w * wdvdY);
-                float cx  = c0 * fx - ddb.x * b0 - ddb.z * b1;
-                float cy  = c0 * fy - ddb.y * b0 - ddb.w * b1;
-                float cxy = iw * (ddb.x * datdX + ddb.y * datdY);
-                float czw = iw * (ddb.z * datdX + ddb.w * datdY);
-
-                gp0x += c0 * y12 - cy * w12              + czw * p2y                                               + ddb.w * p2.w;
-                gp1x += c0 * y20 - cy * w20 - cxy * p2y                              - ddb.y * p2.w;
-                gp2x += c0 * y01 - cy * w01 + cxy * p1y  - czw * p0y                 + ddb.y * p1.w                - ddb.w * p0.w;
-                gp0y += cx * w12 - c0 * x12              - czw * p2x                                - ddb.z * p2.w;
-                gp1y += cx * w20 - c0 * x20 + cxy * p2x               + ddb.x * p2.w;
-                gp2y += cx * w01 - c0 * x01 - cxy * p1x  + czw * p0x  - ddb.x * p1.w                + ddb.z * p0.w;
-                gp0w += cy * x12 - cx * y12              - czw * a1p0                               + ddb.z * p2.y - ddb.w * p2.x;
-                gp1w += cy * x20 - cx * y20 - cxy * a0p1              - ddb.x * p2.y + ddb.y * p2.x;
-                gp2w += cy * x01 - cx * y01 - cxy * a0p2 - czw * a1p2 + ddb.x * p1.y - ddb.y * p1.x - ddb.z * p0.y + ddb.w * p0.x;
+                ro[u] = ld_stream_f4((const float4*)p.rast + img + r);
+                dy[u] = ld_stream_f2((const float2*)p.dy + (img + r) * 2);
+                if (ENABLE_DB) ddb[u] = ld_stream_f4((const float4*)p.ddb + img + r);
             }
-            g[0] = gp0x; g[1] = gp0y; g[2] = gp0w;
-            g[3] = gp1x; g[4] = gp1y; g[5] = gp1w;
-            g[6] = gp2x; g[7] = gp2y; g[8] = gp2w;
         }
-
-        // one atomic per (run of equal triangles, value) instead of one per pixel
-        WarpRuns runs = warp_runs(triIdx);
         #pragma unroll
-        for (int i = 0; i < 9; i++) g[i] = warp_run_sum(g[i], runs);
-        if (runs.is_head && triIdx >= 0)
+        for (int u = 0; u < RG_UNROLL; u++)
         {
-            red_add(acc + 4 * vi0 + 0, g[0]); red_add(acc + 4 * vi0 + 1, g[1]); red_add(acc + 4 * vi0 + 3, g[2]);
-            red_add(acc + 4 * vi1 + 0, g[3]); red_add(acc + 4 * vi1 + 1, g[4]); red_add(acc + 4 * vi1 + 3, g[5]);
-            red_add(acc + 4 * vi2 + 0, g[6]); red_add(acc + 4 * vi2 + 1, g[7]); red_add(acc + 4 * vi2 + 3, g[8]);
+            int g = g0 + u * wstride;
+            if (g >= groups) continue;                      // warp-uniform
+            int r = g * 32 + lane;
+            int triIdx = inb[u] ? float_to_triidx(ro[u].w) - 1 : -1;
+            if (triIdx < 0 || triIdx >= p.T) triIdx = -1;
+            int grad_all_dy = __float_as_int(dy[u].x) | __float_as_int(dy[u].y);
+            int grad_all_ddb = ENABLE_DB ? (__float_as_int(ddb[u].x) | __float_as_int(ddb[u].y) | __float_as_int(ddb[u].z) | __float_as_int(ddb[u].w)) : 0;
+            if (((grad_all_dy | grad_all_ddb) << 1) == 0) triIdx = -1;     // all incoming gradients are +-0
+            int vi0 = 0, vi1 = 0, vi2 = 0;
+            if (triIdx >= 0)
+            {
+                vi0 = __ldg(p.tri + triIdx * 3 + 0); vi1 = __ldg(p.tri + triIdx * 3 + 1); vi2 = __ldg(p.tri + triIdx * 3 + 2);
+                if (vi0 < 0 || vi0 >= p.V || vi1 < 0 || vi1 >= p.V || vi2 < 0 || vi2 >= p.V) triIdx = -1;
+            }
+            if (__all_sync(0xffffffffu, triIdx < 0)) continue;
+
+            float gv[9];
+            #pragma unroll
+            for (int i = 0; i < 9; i++) gv[i] = 0.f;
+            if (triIdx >= 0)
+            {
+                int py = r / p.W, px = r - py * p.W;
+                raster_grad_pixel<ENABLE_DB>(p, n, px, py, vi0, vi1, vi2, dy[u], ddb[u], (grad_all_ddb << 1) != 0, gv);
+            }
+            // one atomic per (run of equal triangles, value) instead of one per pixel
+            WarpRuns runs = warp_runs(triIdx);
+            #pragma unroll
+            for (int i = 0; i < 9; i++) gv[i] = warp_run_sum(gv[i], runs);
+            if (runs.is_head && triIdx >= 0)
+            {
+                red_add(acc + 4 * vi0 + 0, gv[0]); red_add(acc + 4 * vi0 + 1, gv[1]); red_add(acc + 4 * vi0 + 3, gv[2]);
+                red_add(acc + 4 * vi1 + 0, gv[3]); red_add(acc + 4 * vi1 + 1, gv[4]); red_add(acc + 4 * vi1 + 3, gv[5]);
+                red_add(acc + 4 * vi2 + 0, gv[6]); red_add(acc + 4 * vi2 + 1, gv[7]); red_add(acc + 4 * vi2 + 3, gv[8]);
+            }
         }
     }
 
@@ -992,6 +1018,7 @@ extern "C" int b200dr_rasterize_grad(const float* pos, const int32_t* tri, const
     B200DR_CHECK((((uintptr_t)dy) & 7) == 0, "rasterize_grad(): dy input tensor not aligned to float2");
     B200DR_CHECK(B200DR_ALIGNED16(ddb), "rasterize_grad(): ddb input tensor not aligned to float4");
     B200DR_CHECK(N <= 65535, "rasterize_grad(): minibatch size above 65535 is not supported");
+    B200DR_CHECK((size_t)H * W < (1u << 30), "rasterize_grad(): image too large");
 
     RastGradParams p = {};
     p.pos = pos; p.tri = tri; p.rast = rast; p.dy = dy; p.ddb = ddb; p.grad = grad_pos;
@@ -1005,7 +1032,8 @@ extern "C" int b200dr_rasterize_grad(const float* pos, const int32_t* tri, const
     // Persistent-ish grid: enough CTAs to fill the machine, few enough that the shared-memory flush stays negligible.
     int target = b200dr_num_sms() * 4;
     int gx = p.use_smem ? (target + N - 1) / N : 16384;
-    if (gx > p.chunks) gx = p.chunks;
+    int max_gx = (p.chunks + RG_UNROLL - 1) / RG_UNROLL;        // 256-pixel chunks = 8 warp groups per CTA pass
+    if (gx > max_gx) gx = max_gx;
     if (gx < 1) gx = 1;
     dim3 grid(gx, N);
     size_t dyn = p.use_smem ? smem : 0;

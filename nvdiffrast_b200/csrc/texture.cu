@@ -83,14 +83,28 @@ static __device__ __forceinline__ float2 index_linear(const TexParams& p, float 
 
 // texture_kernel.cu:477-585 (2-D).  WANT_DW: also the derivative of the (unclamped) level w.r.t. uv_da.
 template <bool WANT_DW>
+static __device__ __forceinline__ void mip_level_from(const TexParams& p, float4 q, float bias, int& level0, int& level1, float& flevel, float4& dw);
+
+template <bool WANT_DW>
 static __device__ __forceinline__ void mip_level(const TexParams& p, size_t pidx, int& level0, int& level1, float& flevel, float4& dw)
+{
+    level0 = 0; level1 = 0; flevel = 0.f;
+    if (p.filter == B200DR_FILTER_NEAREST || p.filter == B200DR_FILTER_LINEAR) return;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.uv_da) q = ld_stream_f4((const float4*)p.uv_da + pidx);
+    float bias = p.bias ? ld_stream_f(p.bias + pidx) : 0.f;
+    mip_level_from<WANT_DW>(p, q, bias, level0, level1, flevel, dw);
+}
+
+// same, with the pixel's uv_da / bias values already in registers
+template <bool WANT_DW>
+static __device__ __forceinline__ void mip_level_from(const TexParams& p, float4 q, float bias, int& level0, int& level1, float& flevel, float4& dw)
 {
     level0 = 0; level1 = 0; flevel = 0.f;
     if (p.filter == B200DR_FILTER_NEAREST || p.filter == B200DR_FILTER_LINEAR) return;
     float fl = 0.f;
     if (p.uv_da)
     {
-        float4 q = ld_stream_f4((const float4*)p.uv_da + pidx);
         float uscl = (float)p.texW, vscl = (float)p.texH;
         float dsdx = q.x * uscl, dsdy = q.y * uscl, dtdx = q.z * vscl, dtdy = q.w * vscl;
         float A = dsdx * dsdx + dtdx * dtdx;
@@ -111,7 +125,7 @@ static __device__ __forceinline__ void mip_level(const TexParams& p, size_t pidx
         }
         fl = .5f * __log2f(lenMajorSqr);
     }
-    if (p.bias) fl += ld_stream_f(p.bias + pidx);
+    if (p.bias) fl += bias;
     fl = fminf(fmaxf(fl, 0.f), (float)p.mip_max);
     level0 = __float2int_rd(fl);
     if (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && fl > 0.f)
@@ -476,6 +490,8 @@ static __device__ __forceinline__ void unpack4(float4 v, float (&o)[C])
     if (C > 3) o[3 % C] = v.w;
 }
 
+#define TEXF_UNROLL 2
+
 template <int C>
 __global__ void __launch_bounds__(TEX_THREADS) texture_fwd_fast(const TexParams p)
 {
@@ -486,43 +502,63 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_fwd_fast(const TexParams 
     const size_t total = hw * p.N;
     const size_t groups = (total + 31) >> 5;
     const size_t wstride = (size_t)gridDim.x * (TEX_THREADS / 32);
+    const bool mip = (p.filter == B200DR_FILTER_LINEAR_MIPMAP_NEAREST || p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
 
-    for (size_t g = (size_t)blockIdx.x * (TEX_THREADS / 32) + warp; g < groups; g += wstride)
+    for (size_t g0 = (size_t)blockIdx.x * (TEX_THREADS / 32) + warp; g0 < groups; g0 += TEXF_UNROLL * wstride)
     {
-        size_t pidx = g * 32 + lane;
-        bool inb = pidx < total;
-        float o[C];
+        // issue the streaming loads of both groups first
+        float2 uv[TEXF_UNROLL]; float4 da[TEXF_UNROLL]; float bias[TEXF_UNROLL]; bool inb[TEXF_UNROLL];
         #pragma unroll
-        for (int i = 0; i < C; i++) o[i] = 0.f;
-        if (inb)
+        for (int u = 0; u < TEXF_UNROLL; u++)
         {
-            float2 uv = ld_stream_f2((const float2*)p.uv + pidx);
-            int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
-            if (p.filter == B200DR_FILTER_NEAREST)
+            size_t pidx = (g0 + u * wstride) * 32 + lane;
+            inb[u] = (g0 + u * wstride < groups) && (pidx < total);
+            uv[u] = make_float2(0.f, 0.f); da[u] = make_float4(0.f, 0.f, 0.f, 0.f); bias[u] = 0.f;
+            if (inb[u])
             {
-                unpack4<C>(texel4(p.tex[0], index_nearest(p, uv.x, uv.y, tz), 4, 0), o);
-            }
-            else
-            {
-                int level0, level1; float flevel; float4 dw;
-                mip_level<false>(p, pidx, level0, level1, flevel, dw);
-                int4 tc0;
-                float2 uv0 = index_linear(p, uv.x, uv.y, tz, level0, tc0);
-                const float* t0 = p.tex[level0];
-                float4 a = bilerp4(texel4(t0, tc0.x, 4, 0), texel4(t0, tc0.y, 4, 0), texel4(t0, tc0.z, 4, 0), texel4(t0, tc0.w, 4, 0), uv0);
-                if (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && flevel > 0.f)
-                {
-                    int4 tc1;
-                    float2 uv1 = index_linear(p, uv.x, uv.y, tz, level1, tc1);
-                    const float* t1 = p.tex[level1];
-                    float4 b = bilerp4(texel4(t1, tc1.x, 4, 0), texel4(t1, tc1.y, 4, 0), texel4(t1, tc1.z, 4, 0), texel4(t1, tc1.w, 4, 0), uv1);
-                    a = make_float4(lerpf(a.x, b.x, flevel), lerpf(a.y, b.y, flevel), lerpf(a.z, b.z, flevel), lerpf(a.w, b.w, flevel));
-                }
-                unpack4<C>(a, o);
+                uv[u] = ld_stream_f2((const float2*)p.uv + pidx);
+                if (mip && p.uv_da) da[u] = ld_stream_f4((const float4*)p.uv_da + pidx);
+                if (mip && p.bias) bias[u] = ld_stream_f(p.bias + pidx);
             }
         }
-        bool full = (g * 32 + 32 <= total);
-        warp_store_aos<C>(p.out + g * 32 * C, o, lane, inb, full, s_stage[warp]);
+        #pragma unroll
+        for (int u = 0; u < TEXF_UNROLL; u++)
+        {
+            size_t g = g0 + u * wstride;
+            if (g >= groups) continue;                  // warp-uniform
+            size_t pidx = g * 32 + lane;
+            float o[C];
+            #pragma unroll
+            for (int i = 0; i < C; i++) o[i] = 0.f;
+            if (inb[u])
+            {
+                int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
+                if (p.filter == B200DR_FILTER_NEAREST)
+                {
+                    unpack4<C>(texel4(p.tex[0], index_nearest(p, uv[u].x, uv[u].y, tz), 4, 0), o);
+                }
+                else
+                {
+                    int level0, level1; float flevel; float4 dw;
+                    mip_level_from<false>(p, da[u], bias[u], level0, level1, flevel, dw);
+                    int4 tc0;
+                    float2 uv0 = index_linear(p, uv[u].x, uv[u].y, tz, level0, tc0);
+                    const float* t0 = p.tex[level0];
+                    float4 a = bilerp4(texel4(t0, tc0.x, 4, 0), texel4(t0, tc0.y, 4, 0), texel4(t0, tc0.z, 4, 0), texel4(t0, tc0.w, 4, 0), uv0);
+                    if (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && flevel > 0.f)
+                    {
+                        int4 tc1;
+                        float2 uv1 = index_linear(p, uv[u].x, uv[u].y, tz, level1, tc1);
+                        const float* t1 = p.tex[level1];
+                        float4 b = bilerp4(texel4(t1, tc1.x, 4, 0), texel4(t1, tc1.y, 4, 0), texel4(t1, tc1.z, 4, 0), texel4(t1, tc1.w, 4, 0), uv1);
+                        a = make_float4(lerpf(a.x, b.x, flevel), lerpf(a.y, b.y, flevel), lerpf(a.z, b.z, flevel), lerpf(a.w, b.w, flevel));
+                    }
+                    unpack4<C>(a, o);
+                }
+            }
+            bool full = (g * 32 + 32 <= total);
+            warp_store_aos<C>(p.out + g * 32 * C, o, lane, inb[u], full, s_stage[warp]);
+        }
     }
 }
 
@@ -559,7 +595,7 @@ static __device__ __forceinline__ void scatter_tap(float* g, int level, int tc, 
 }
 
 template <int C>
-__global__ void __launch_bounds__(TEX_THREADS) texture_grad_fast(const TexParams p)
+__global__ void __launch_bounds__(TEX_THREADS, 4) texture_grad_fast(const TexParams p)
 {
     constexpr int SK = (C == 3) ? 3 : 1;
     __shared__ __align__(16) float s_stage[TEX_THREADS / 32][32 * SK];
@@ -582,6 +618,15 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_grad_fast(const TexParams
         float dy[C];
         #pragma unroll
         for (int i = 0; i < C; i++) dy[i] = 0.f;
+        // every streaming load of the group is issued before the first use (dy decides `act`, but waiting for it before
+        // fetching uv / uv_da would serialise two DRAM round trips)
+        float2 uv = make_float2(0.f, 0.f); float4 da = make_float4(0.f, 0.f, 0.f, 0.f); float bias = 0.f;
+        if (inb)
+        {
+            uv = ld_stream_f2((const float2*)p.uv + pidx);
+            if (p.uv_da) da = ld_stream_f4((const float4*)p.uv_da + pidx);
+            if (p.bias) bias = ld_stream_f(p.bias + pidx);
+        }
         warp_load_aos<C>(p.dy + g * 32 * C, dy, lane, inb, full, s_stage[warp]);
         unsigned dmax = 0u;
         #pragma unroll
@@ -600,11 +645,10 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_grad_fast(const TexParams
             if (act)
             {
                 int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
-                float2 uv = ld_stream_f2((const float2*)p.uv + pidx);
                 if (p.filter == B200DR_FILTER_NEAREST) tc0.x = index_nearest(p, uv.x, uv.y, tz);
                 else
                 {
-                    mip_level<true>(p, pidx, level0, level1, flevel, dw);
+                    mip_level_from<true>(p, da, bias, level0, level1, flevel, dw);
                     uv0 = index_linear(p, uv.x, uv.y, tz, level0, tc0);
                     two = trilinear && (flevel > 0.f);
                     f0 = trilinear ? (1.f - flevel) : 1.f;
