@@ -13,6 +13,7 @@
 // (REDG.E.ADD.F32x4: one atomic per texel instead of one per texel channel), then a resolve pass pulls the mip levels
 // down to the base level and writes the gradient in the caller's channel layout.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -28,6 +29,7 @@ struct TexParams
     int N, H, W, texD, texH, texW, C, Cp;
     int filter, boundary, mip_max;
     int staged;
+    int dbg;                                // B200DR_TEXDBG experiment switches (0 in production)
     int chunks;                             // 256-pixel chunks over the flat N*H*W pixel array
 };
 
@@ -570,45 +572,53 @@ static __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
-// One bilinear tap of the texel-gradient scatter.  uniform: the whole warp sits on this texel with the same weight, `dysum`
-// is the warp-summed incoming gradient; lane 0 adds it to the CTA's hot-texel cache (or to memory if the slot is taken).
+// One bilinear tap of the texel-gradient scatter: a 128-bit vector reduction per lane.
 template <int C>
-static __device__ __forceinline__ void scatter_tap(float* g, int level, int tc, float w, const float (&dy)[C], bool uniform,
-                                                   const float (&dysum)[C], HotCache* hot, int slot, int lane)
+static __device__ __forceinline__ void scatter_tap(float* g, int tc, float w, const float (&dy)[C])
 {
     if (tc < 0) return;
-    float* q = g + (size_t)tc * 4;
-    if (!uniform)
+    red_add4(g + (size_t)tc * 4, make_float4(w * dy[0], (C > 1) ? w * dy[1 % C] : 0.f, (C > 2) ? w * dy[2 % C] : 0.f, (C > 3) ? w * dy[3 % C] : 0.f));
+}
+
+// Pending contribution of "uniform" pixel groups (all 32 pixels on the same texel quad with the same weights: constant uv,
+// typically the background).  A warp keeps the summed incoming gradient of consecutive uniform groups in registers and
+// issues the four tap reductions only when the quad changes or the kernel ends: instead of one same-address atomic per
+// pixel (serialised chip-wide at ~0.85 clk each) the texel sees a handful per warp.
+template <int C>
+struct Pending
+{
+    int key; int u, v;          // identity: texel quad (tc0.x ^ level << 27) and the bit patterns of the bilinear weights
+    int level; int4 tc; float4 w;
+    float sum[C];
+};
+
+template <int C>
+static __device__ __forceinline__ void pending_flush(Pending<C>& pd, const TexParams& p, int lane)
+{
+    if (pd.key != -1 && lane < 4)
     {
-        red_add4(q, make_float4(w * dy[0], (C > 1) ? w * dy[1 % C] : 0.f, (C > 2) ? w * dy[2 % C] : 0.f, (C > 3) ? w * dy[3 % C] : 0.f));
-        return;
+        int tc = (lane == 0) ? pd.tc.x : (lane == 1) ? pd.tc.y : (lane == 2) ? pd.tc.z : pd.tc.w;
+        float w = (lane == 0) ? pd.w.x : (lane == 1) ? pd.w.y : (lane == 2) ? pd.w.z : pd.w.w;
+        scatter_tap<C>(p.gpad[pd.level], tc, w, pd.sum);
     }
-    if (lane != 0) return;
-    float4 v = make_float4(w * dysum[0], (C > 1) ? w * dysum[1 % C] : 0.f, (C > 2) ? w * dysum[2 % C] : 0.f, (C > 3) ? w * dysum[3 % C] : 0.f);
-    int key = tc ^ (level << 27);
-    int old = (slot >= 0) ? atomicCAS(&hot->key[slot], -1, key) : 0;
-    if (slot >= 0 && (old == -1 || old == key))
-    {
-        atomicAdd(&hot->val[slot][0], v.x); atomicAdd(&hot->val[slot][1], v.y); atomicAdd(&hot->val[slot][2], v.z); atomicAdd(&hot->val[slot][3], v.w);
-    }
-    else red_add4(q, v);
+    pd.key = -1;
 }
 
 template <int C>
-__global__ void __launch_bounds__(TEX_THREADS, 4) texture_grad_fast(const TexParams p)
+__global__ void __launch_bounds__(TEX_THREADS, 3) texture_grad_fast(const TexParams p)
 {
     constexpr int SK = (C == 3) ? 3 : 1;
     __shared__ __align__(16) float s_stage[TEX_THREADS / 32][32 * SK];
-    __shared__ HotCache s_hot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t hw = (size_t)p.H * p.W;
     const size_t total = hw * p.N;
     const size_t groups = (total + 31) >> 5;
     const size_t wstride = (size_t)gridDim.x * (TEX_THREADS / 32);
     const bool trilinear = (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
-    if (tid < TEX_HOT_SLOTS) s_hot.key[tid] = -1;
-    if (tid < TEX_HOT_SLOTS * TEX_HOT_MAXC) s_hot.val[tid / TEX_HOT_MAXC][tid % TEX_HOT_MAXC] = 0.f;
-    __syncthreads();
+    Pending<C> pd;
+    pd.key = -1; pd.u = 0; pd.v = 0; pd.level = 0; pd.tc = make_int4(-1, -1, -1, -1); pd.w = make_float4(0.f, 0.f, 0.f, 0.f);
+    #pragma unroll
+    for (int i = 0; i < C; i++) pd.sum[i] = 0.f;
 
     for (size_t g = (size_t)blockIdx.x * (TEX_THREADS / 32) + warp; g < groups; g += wstride)
     {
@@ -655,72 +665,85 @@ __global__ void __launch_bounds__(TEX_THREADS, 4) texture_grad_fast(const TexPar
                     if (two) uv1 = index_linear(p, uv.x, uv.y, tz, level1, tc1);
                 }
             }
-            // Whole warp on one texel quad with identical weights (constant uv, e.g. background)?  Then reduce dy once.
-            int key0 = act ? (tc0.x ^ (level0 << 27)) : -1;
-            // (shuffles are evaluated by every lane BEFORE the boolean expression: no short-circuit around warp collectives)
-            int k0 = __shfl_sync(0xffffffffu, key0, 0);
-            int u0 = __shfl_sync(0xffffffffu, __float_as_int(uv0.x), 0);
-            int v0 = __shfl_sync(0xffffffffu, __float_as_int(uv0.y), 0);
-            bool same = act && !two && (key0 == k0) && (__float_as_int(uv0.x) == u0) && (__float_as_int(uv0.y) == v0);
-            bool uniform = __all_sync(0xffffffffu, same);
-            float dysum[C];
-            #pragma unroll
-            for (int i = 0; i < C; i++) dysum[i] = uniform ? warp_sum(dy[i]) : 0.f;
+            float uv011 = uv0.x * uv0.y, uv010 = uv0.x - uv011, uv001 = uv0.y - uv011, uv000 = 1.f - uv0.x - uv001;
+            float4 w0 = (p.filter == B200DR_FILTER_NEAREST) ? make_float4(1.f, 0.f, 0.f, 0.f)
+                                                            : make_float4(uv000 * f0, uv010 * f0, uv001 * f0, uv011 * f0);
 
-            if (p.filter == B200DR_FILTER_NEAREST)
+            // Whole warp on one texel quad with identical weights?  (shuffles first: no short-circuit around collectives)
+            int key0 = act ? (tc0.x ^ (level0 << 27)) : -1;
+            int k0 = __shfl_sync(0xffffffffu, key0, 0);
+            int u0 = __shfl_sync(0xffffffffu, __float_as_int(w0.y), 0);
+            int v0 = __shfl_sync(0xffffffffu, __float_as_int(w0.z), 0);
+            bool same = act && !two && (key0 == k0) && (__float_as_int(w0.y) == u0) && (__float_as_int(w0.z) == v0);
+            bool uniform = __all_sync(0xffffffffu, same);
+            if (uniform)
             {
-                scatter_tap<C>(p.gpad[0], 0, tc0.x, 1.f, dy, uniform, dysum, &s_hot, 0, lane);
+                if (!(p.dbg & 2))
+                {
+                    if (pd.key != key0 || pd.u != u0 || pd.v != v0)
+                    {
+                        pending_flush<C>(pd, p, lane);
+                        pd.key = key0; pd.u = u0; pd.v = v0; pd.level = level0; pd.tc = tc0; pd.w = w0;
+                        #pragma unroll
+                        for (int i = 0; i < C; i++) pd.sum[i] = 0.f;
+                    }
+                    #pragma unroll
+                    for (int i = 0; i < C; i++) pd.sum[i] += warp_sum(dy[i]);
+                }
             }
-            else
+            else if (!(p.dbg & 1))
             {
-                float uv011 = uv0.x * uv0.y, uv010 = uv0.x - uv011, uv001 = uv0.y - uv011, uv000 = 1.f - uv0.x - uv001;
                 float* g0 = p.gpad[level0];
-                scatter_tap<C>(g0, level0, tc0.x, uv000 * f0, dy, uniform, dysum, &s_hot, 0, lane);
-                scatter_tap<C>(g0, level0, tc0.y, uv010 * f0, dy, uniform, dysum, &s_hot, 1, lane);
-                scatter_tap<C>(g0, level0, tc0.z, uv001 * f0, dy, uniform, dysum, &s_hot, 2, lane);
-                scatter_tap<C>(g0, level0, tc0.w, uv011 * f0, dy, uniform, dysum, &s_hot, 3, lane);
+                scatter_tap<C>(g0, tc0.x, w0.x, dy);
+                if (p.filter != B200DR_FILTER_NEAREST)
+                {
+                    scatter_tap<C>(g0, tc0.y, w0.y, dy);
+                    scatter_tap<C>(g0, tc0.z, w0.z, dy);
+                    scatter_tap<C>(g0, tc0.w, w0.w, dy);
+                    if (two)
+                    {
+                        float uv111 = uv1.x * uv1.y, uv110 = uv1.x - uv111, uv101 = uv1.y - uv111, uv100 = 1.f - uv1.x - uv101;
+                        float* g1 = p.gpad[level1];
+                        scatter_tap<C>(g1, tc1.x, uv100 * flevel, dy);
+                        scatter_tap<C>(g1, tc1.y, uv110 * flevel, dy);
+                        scatter_tap<C>(g1, tc1.z, uv101 * flevel, dy);
+                        scatter_tap<C>(g1, tc1.w, uv111 * flevel, dy);
+                    }
+                }
+            }
+
+            if (act && p.filter != B200DR_FILTER_NEAREST && !(p.dbg & 4))
+            {
+                const float* t0 = p.tex[level0];
+                float sclu0 = (float)lvl_w(p, level0), sclv0 = (float)lvl_h(p, level0);
+                float a00[C], a10[C], a01[C], a11[C];
+                unpack4<C>(texel4(t0, tc0.x, 4, 0), a00); unpack4<C>(texel4(t0, tc0.y, 4, 0), a10);
+                unpack4<C>(texel4(t0, tc0.z, 4, 0), a01); unpack4<C>(texel4(t0, tc0.w, 4, 0), a11);
+                #pragma unroll
+                for (int i = 0; i < C; i++)
+                {
+                    float dy0 = f0 * dy[i];
+                    float ad = (a11[i] + a00[i] - a10[i] - a01[i]);
+                    gu += dy0 * ((a10[i] - a00[i]) + uv0.y * ad) * sclu0;
+                    gv += dy0 * ((a01[i] - a00[i]) + uv0.x * ad) * sclv0;
+                }
                 if (two)
                 {
-                    float uv111 = uv1.x * uv1.y, uv110 = uv1.x - uv111, uv101 = uv1.y - uv111, uv100 = 1.f - uv1.x - uv101;
-                    float* g1 = p.gpad[level1];
-                    scatter_tap<C>(g1, level1, tc1.x, uv100 * flevel, dy, false, dysum, &s_hot, -1, lane);
-                    scatter_tap<C>(g1, level1, tc1.y, uv110 * flevel, dy, false, dysum, &s_hot, -1, lane);
-                    scatter_tap<C>(g1, level1, tc1.z, uv101 * flevel, dy, false, dysum, &s_hot, -1, lane);
-                    scatter_tap<C>(g1, level1, tc1.w, uv111 * flevel, dy, false, dysum, &s_hot, -1, lane);
-                }
-                if (act)
-                {
-                    const float* t0 = p.tex[level0];
-                    float sclu0 = (float)lvl_w(p, level0), sclv0 = (float)lvl_h(p, level0);
-                    float a00[C], a10[C], a01[C], a11[C];
-                    unpack4<C>(texel4(t0, tc0.x, 4, 0), a00); unpack4<C>(texel4(t0, tc0.y, 4, 0), a10);
-                    unpack4<C>(texel4(t0, tc0.z, 4, 0), a01); unpack4<C>(texel4(t0, tc0.w, 4, 0), a11);
+                    const float* t1 = p.tex[level1];
+                    float sclu1 = (float)lvl_w(p, level1), sclv1 = (float)lvl_h(p, level1);
+                    float b00[C], b10[C], b01[C], b11[C];
+                    unpack4<C>(texel4(t1, tc1.x, 4, 0), b00); unpack4<C>(texel4(t1, tc1.y, 4, 0), b10);
+                    unpack4<C>(texel4(t1, tc1.z, 4, 0), b01); unpack4<C>(texel4(t1, tc1.w, 4, 0), b11);
                     #pragma unroll
                     for (int i = 0; i < C; i++)
                     {
-                        float dy0 = f0 * dy[i];
-                        float ad = (a11[i] + a00[i] - a10[i] - a01[i]);
-                        gu += dy0 * ((a10[i] - a00[i]) + uv0.y * ad) * sclu0;
-                        gv += dy0 * ((a01[i] - a00[i]) + uv0.x * ad) * sclv0;
-                    }
-                    if (two)
-                    {
-                        const float* t1 = p.tex[level1];
-                        float sclu1 = (float)lvl_w(p, level1), sclv1 = (float)lvl_h(p, level1);
-                        float b00[C], b10[C], b01[C], b11[C];
-                        unpack4<C>(texel4(t1, tc1.x, 4, 0), b00); unpack4<C>(texel4(t1, tc1.y, 4, 0), b10);
-                        unpack4<C>(texel4(t1, tc1.z, 4, 0), b01); unpack4<C>(texel4(t1, tc1.w, 4, 0), b11);
-                        #pragma unroll
-                        for (int i = 0; i < C; i++)
-                        {
-                            float dy1 = flevel * dy[i];
-                            float bd = (b11[i] + b00[i] - b10[i] - b01[i]);
-                            gu += dy1 * ((b10[i] - b00[i]) + uv1.y * bd) * sclu1;
-                            gv += dy1 * ((b01[i] - b00[i]) + uv1.x * bd) * sclv1;
-                            float a = bilerp(a00[i], a10[i], a01[i], a11[i], uv0);
-                            float b = bilerp(b00[i], b10[i], b01[i], b11[i], uv1);
-                            df += (b - a) * dy[i];
-                        }
+                        float dy1 = flevel * dy[i];
+                        float bd = (b11[i] + b00[i] - b10[i] - b01[i]);
+                        gu += dy1 * ((b10[i] - b00[i]) + uv1.y * bd) * sclu1;
+                        gv += dy1 * ((b01[i] - b00[i]) + uv1.x * bd) * sclv1;
+                        float a = bilerp(a00[i], a10[i], a01[i], a11[i], uv0);
+                        float b = bilerp(b00[i], b10[i], b01[i], b11[i], uv1);
+                        df += (b - a) * dy[i];
                     }
                 }
             }
@@ -732,17 +755,7 @@ __global__ void __launch_bounds__(TEX_THREADS, 4) texture_grad_fast(const TexPar
             if (p.g_uv_da) st_stream_f4((float4*)p.g_uv_da + pidx, make_float4(dw.x * df, dw.y * df, dw.z * df, dw.w * df));
         }
     }
-
-    __syncthreads();
-    if (tid < TEX_HOT_SLOTS)
-    {
-        int key = s_hot.key[tid];
-        if (key != -1)
-        {
-            int level = (int)((unsigned)key >> 27), tc = key & ((1 << 27) - 1);
-            red_add4(p.gpad[level] + (size_t)tc * 4, make_float4(s_hot.val[tid][0], s_hot.val[tid][1], s_hot.val[tid][2], s_hot.val[tid][3]));
-        }
-    }
+    pending_flush<C>(pd, p, lane);
 }
 
 // Resolve: g_out[texel][c] = pad[0][texel][c] (+ sum over levels of weight * pad[L][parent texel][c] when pulling mips),
@@ -965,6 +978,7 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
         }
     }
 
+    { const char* e = getenv("B200DR_TEXDBG"); p.dbg = e ? atoi(e) : 0; }
     if (C <= 4 && B200DR_ALIGNED16(dy))
     {
         size_t groups = ((size_t)N * H * W + 31) / 32;
