@@ -247,6 +247,31 @@ static __device__ __forceinline__ void coop_load(float* __restrict__ s, const fl
     if (tid < n - done) s[done + tid] = ld_stream_f(g + done + tid);
 }
 
+// Runs capped at 4 lanes (an extra head every 4 lanes): two shuffle steps instead of five.  Used where a 2-4x cut in
+// the number of atomics is what matters (duplicate texels of neighbouring pixels), not a full 32-lane reduction.
+static __device__ __forceinline__ WarpRuns warp_runs_max4(int key, int key2)
+{
+    const int lane = threadIdx.x & 31;
+    int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    int prev2 = __shfl_up_sync(0xffffffffu, key2, 1);
+    bool head = ((lane & 3) == 0) || (prev != key) || (prev2 != key2);
+    WarpRuns r;
+    r.heads = __ballot_sync(0xffffffffu, head);
+    unsigned above = (lane == 31) ? 0u : (r.heads >> (lane + 1));
+    r.run_end = above ? (lane + __ffs(above)) : 32;
+    r.is_head = head;
+    return r;
+}
+static __device__ __forceinline__ float warp_run_sum_max4(float v, const WarpRuns& r)
+{
+    const int lane = threadIdx.x & 31;
+    float t = __shfl_down_sync(0xffffffffu, v, 1);
+    if (lane + 1 < r.run_end) v += t;
+    t = __shfl_down_sync(0xffffffffu, v, 2);
+    if (lane + 2 < r.run_end) v += t;
+    return v;
+}
+
 // fp32 add without return value (RED).  Works on shared and global addresses.
 static __device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
 // 128-bit vector reduction (global memory only, 16-byte aligned): REDG.E.ADD.F32x4 on sm_100a.

@@ -693,22 +693,36 @@ __global__ void __launch_bounds__(TEX_THREADS, 3) texture_grad_fast(const TexPar
             }
             else if (!(p.dbg & 1))
             {
+                // Neighbouring pixels of a magnified texture sit on the same texel quad: sum runs of up to 4 equal quads
+                // with two shuffle steps, so a quad receives one vector reduction per run instead of one per pixel
+                // (same-address reductions inside one instruction serialise).  Skipped when the warp has few duplicates.
+                WarpRuns runs = warp_runs_max4(act && !two ? key0 : -1 - lane, tc0.w);    // first and diagonal tap pin the whole quad
+                const bool merge = !(p.dbg & 8) && (__popc(runs.heads) <= 24);
                 float* g0 = p.gpad[level0];
-                scatter_tap<C>(g0, tc0.x, w0.x, dy);
-                if (p.filter != B200DR_FILTER_NEAREST)
+                const int ntap = (p.filter == B200DR_FILTER_NEAREST) ? 1 : 4;
+                for (int t = 0; t < ntap; t++)
                 {
-                    scatter_tap<C>(g0, tc0.y, w0.y, dy);
-                    scatter_tap<C>(g0, tc0.z, w0.z, dy);
-                    scatter_tap<C>(g0, tc0.w, w0.w, dy);
-                    if (two)
+                    int tc = (t == 0) ? tc0.x : (t == 1) ? tc0.y : (t == 2) ? tc0.z : tc0.w;
+                    float w = (t == 0) ? w0.x : (t == 1) ? w0.y : (t == 2) ? w0.z : w0.w;
+                    float v[C];
+                    #pragma unroll
+                    for (int i = 0; i < C; i++) v[i] = act ? w * dy[i] : 0.f;
+                    if (merge)
                     {
-                        float uv111 = uv1.x * uv1.y, uv110 = uv1.x - uv111, uv101 = uv1.y - uv111, uv100 = 1.f - uv1.x - uv101;
-                        float* g1 = p.gpad[level1];
-                        scatter_tap<C>(g1, tc1.x, uv100 * flevel, dy);
-                        scatter_tap<C>(g1, tc1.y, uv110 * flevel, dy);
-                        scatter_tap<C>(g1, tc1.z, uv101 * flevel, dy);
-                        scatter_tap<C>(g1, tc1.w, uv111 * flevel, dy);
+                        #pragma unroll
+                        for (int i = 0; i < C; i++) v[i] = warp_run_sum_max4(v[i], runs);
+                        if (runs.is_head) scatter_tap<C>(g0, tc, 1.f, v);
                     }
+                    else scatter_tap<C>(g0, tc, 1.f, v);
+                }
+                if (two)
+                {
+                    float uv111 = uv1.x * uv1.y, uv110 = uv1.x - uv111, uv101 = uv1.y - uv111, uv100 = 1.f - uv1.x - uv101;
+                    float* g1 = p.gpad[level1];
+                    scatter_tap<C>(g1, tc1.x, uv100 * flevel, dy);
+                    scatter_tap<C>(g1, tc1.y, uv110 * flevel, dy);
+                    scatter_tap<C>(g1, tc1.z, uv101 * flevel, dy);
+                    scatter_tap<C>(g1, tc1.w, uv111 * flevel, dy);
                 }
             }
 
