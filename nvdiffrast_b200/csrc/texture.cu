@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(TEX_THREADS, 3) texture_grad_fast(const TexPar
                 // Neighbouring pixels of a magnified texture sit on the same texel quad: sum runs of up to 4 equal quads
                 // with two shuffle steps, so a quad receives one vector reduction per run instead of one per pixel
                 // (same-address reductions inside one instruction serialise).  Skipped when the warp has few duplicates.
-                WarpRuns runs = warp_runs_max4(act && !two ? key0 : -1 - lane, tc0.w);    // first and diagonal tap pin the whole quad
+                WarpRuns runs = warp_runs_max4((act && !two && tc0.x >= 0 && tc0.w >= 0) ? key0 : -1 - lane, tc0.w);    // first and diagonal tap pin the whole quad
                 const bool merge = !(p.dbg & 8) && (__popc(runs.heads) <= 24);
                 float* g0 = p.gpad[level0];
                 const int ntap = (p.filter == B200DR_FILTER_NEAREST) ? 1 : 4;
