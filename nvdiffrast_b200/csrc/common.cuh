@@ -151,6 +151,61 @@ static __device__ __forceinline__ void warp_load_aos(const float* base, float (&
     }
 }
 
+// Split form of warp_load_aos for software pipelining: `issue` starts the global loads of a group (results stay in
+// registers), `finish` turns them into the lane's K values (through the warp transpose when K is not a power of two).
+template <int K> struct AosRaw { float4 q[(K == 1 || K == 2 || K == 4) ? 1 : (K == 8 ? 2 : (K * 32 + 127) / 128)]; };
+
+template <int K>
+static __device__ __forceinline__ void warp_load_aos_issue(const float* base, AosRaw<K>& raw, int lane, bool valid, bool full)
+{
+    raw.q[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (K == 1) { if (valid) raw.q[0].x = ld_stream_f(base + lane); }
+    else if (K == 2) { if (valid) { float2 t = ld_stream_f2((const float2*)base + lane); raw.q[0].x = t.x; raw.q[0].y = t.y; } }
+    else if (K == 4) { if (valid) raw.q[0] = ld_stream_f4((const float4*)base + lane); }
+    else if (K == 8) { raw.q[1] = raw.q[0]; if (valid) ld_stream_f8(base + 8 * lane, raw.q[0], raw.q[1]); }
+    else if (full)
+    {
+        #pragma unroll
+        for (int j = 0; j < (K * 32 + 127) / 128; j++)
+        {
+            int q = lane + 32 * j;
+            raw.q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q * 4 < K * 32) raw.q[j] = ld_stream_f4((const float4*)base + q);
+        }
+    }
+}
+
+template <int K>
+static __device__ __forceinline__ void warp_load_aos_finish(const float* base, const AosRaw<K>& raw, float (&v)[K], int lane, bool valid, bool full, float* s)
+{
+    if (K == 1) { v[0] = raw.q[0].x; }
+    else if (K == 2) { v[0] = raw.q[0].x; v[1 % K] = raw.q[0].y; }
+    else if (K == 4) { v[0] = raw.q[0].x; v[1 % K] = raw.q[0].y; v[2 % K] = raw.q[0].z; v[3 % K] = raw.q[0].w; }
+    else if (K == 8)
+    {
+        v[0] = raw.q[0].x; v[1 % K] = raw.q[0].y; v[2 % K] = raw.q[0].z; v[3 % K] = raw.q[0].w;
+        v[4 % K] = raw.q[(K == 8) ? 1 : 0].x; v[5 % K] = raw.q[(K == 8) ? 1 : 0].y; v[6 % K] = raw.q[(K == 8) ? 1 : 0].z; v[7 % K] = raw.q[(K == 8) ? 1 : 0].w;
+    }
+    else if (full)
+    {
+        #pragma unroll
+        for (int j = 0; j < (K * 32 + 127) / 128; j++)
+        {
+            int q = lane + 32 * j;
+            if (q * 4 < K * 32) *(float4*)(s + 4 * q) = raw.q[j];
+        }
+        __syncwarp();
+        #pragma unroll
+        for (int i = 0; i < K; i++) v[i] = s[lane * K + i];
+        __syncwarp();
+    }
+    else
+    {
+        #pragma unroll
+        for (int i = 0; i < K; i++) v[i] = valid ? ld_stream_f(base + lane * K + i) : 0.f;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Warp-level segmented ("run") reduction.
 //

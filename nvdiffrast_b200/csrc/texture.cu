@@ -604,170 +604,195 @@ static __device__ __forceinline__ void pending_flush(Pending<C>& pd, const TexPa
     pd.key = -1;
 }
 
+#define TEXG_THREADS 128
+#define TEXG_UNROLL  2
+
+// Streaming inputs of one 32-pixel group, loaded up front (two groups are in flight per warp).
 template <int C>
-__global__ void __launch_bounds__(TEX_THREADS, 3) texture_grad_fast(const TexParams p)
+struct TexGradIn { AosRaw<C> dy; float2 uv; float4 da; float bias; bool inb, full; size_t g; };
+
+template <int C>
+static __device__ __forceinline__ void texgrad_issue(const TexParams& p, size_t g, size_t groups, size_t total, int lane, TexGradIn<C>& in)
+{
+    in.g = g;
+    size_t pidx = g * 32 + lane;
+    in.inb = (g < groups) && (pidx < total);
+    in.full = (g < groups) && (g * 32 + 32 <= total);
+    in.uv = make_float2(0.f, 0.f); in.da = make_float4(0.f, 0.f, 0.f, 0.f); in.bias = 0.f;
+    if (in.inb)
+    {
+        in.uv = ld_stream_f2((const float2*)p.uv + pidx);
+        if (p.uv_da) in.da = ld_stream_f4((const float4*)p.uv_da + pidx);
+        if (p.bias) in.bias = ld_stream_f(p.bias + pidx);
+    }
+    warp_load_aos_issue<C>(p.dy + g * 32 * C, in.dy, lane, in.inb, in.full);
+}
+
+template <int C>
+static __device__ __forceinline__ void texgrad_group(const TexParams& p, const TexGradIn<C>& in, Pending<C>& pd, int lane, float* sw,
+                                                     size_t hw, bool trilinear)
+{
+    const size_t pidx = in.g * 32 + lane;
+    const bool inb = in.inb;
+    float dy[C];
+    warp_load_aos_finish<C>(p.dy + in.g * 32 * C, in.dy, dy, lane, inb, in.full, sw);
+    unsigned dmax = 0u;
+    #pragma unroll
+    for (int i = 0; i < C; i++) dmax |= __float_as_uint(dy[i]);
+    bool act = inb && (__uint_as_float(dmax) != 0.f);
+    const float2 uv = in.uv;
+
+    float gu = 0.f, gv = 0.f, df = 0.f;
+    float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (__any_sync(0xffffffffu, act))
+    {
+        int level0 = 0, level1 = 0; float flevel = 0.f;
+        int4 tc0 = make_int4(-1, -1, -1, -1), tc1 = tc0;
+        float2 uv0 = make_float2(0.f, 0.f), uv1 = uv0;
+        bool two = false;
+        float f0 = 1.f;
+        if (act)
+        {
+            int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
+            if (p.filter == B200DR_FILTER_NEAREST) tc0.x = index_nearest(p, uv.x, uv.y, tz);
+            else
+            {
+                mip_level_from<true>(p, in.da, in.bias, level0, level1, flevel, dw);
+                uv0 = index_linear(p, uv.x, uv.y, tz, level0, tc0);
+                two = trilinear && (flevel > 0.f);
+                f0 = trilinear ? (1.f - flevel) : 1.f;
+                if (two) uv1 = index_linear(p, uv.x, uv.y, tz, level1, tc1);
+            }
+        }
+        float uv011 = uv0.x * uv0.y, uv010 = uv0.x - uv011, uv001 = uv0.y - uv011, uv000 = 1.f - uv0.x - uv001;
+        float4 w0 = (p.filter == B200DR_FILTER_NEAREST) ? make_float4(1.f, 0.f, 0.f, 0.f)
+                                                        : make_float4(uv000 * f0, uv010 * f0, uv001 * f0, uv011 * f0);
+
+        // Whole warp on one texel quad with identical weights?  (shuffles first: no short-circuit around collectives)
+        int key0 = act ? (tc0.x ^ (level0 << 27)) : -1;
+        int k0 = __shfl_sync(0xffffffffu, key0, 0);
+        int u0 = __shfl_sync(0xffffffffu, __float_as_int(w0.y), 0);
+        int v0 = __shfl_sync(0xffffffffu, __float_as_int(w0.z), 0);
+        bool same = act && !two && (key0 == k0) && (__float_as_int(w0.y) == u0) && (__float_as_int(w0.z) == v0);
+        bool uniform = __all_sync(0xffffffffu, same);
+        if (uniform)
+        {
+            if (!(p.dbg & 2))
+            {
+                if (pd.key != key0 || pd.u != u0 || pd.v != v0)
+                {
+                    pending_flush<C>(pd, p, lane);
+                    pd.key = key0; pd.u = u0; pd.v = v0; pd.level = level0; pd.tc = tc0; pd.w = w0;
+                    #pragma unroll
+                    for (int i = 0; i < C; i++) pd.sum[i] = 0.f;
+                }
+                #pragma unroll
+                for (int i = 0; i < C; i++) pd.sum[i] += warp_sum(dy[i]);
+            }
+        }
+        else if (!(p.dbg & 1))
+        {
+            // Neighbouring pixels of a magnified texture sit on the same texel quad: sum runs of up to 4 equal quads
+            // with two shuffle steps, so a quad receives one vector reduction per run instead of one per pixel
+            // (same-address reductions inside one instruction serialise).  Skipped when the warp has few duplicates.
+            WarpRuns runs = warp_runs_max4((act && !two && tc0.x >= 0 && tc0.w >= 0) ? key0 : -1 - lane, tc0.w);    // first and diagonal tap pin the whole quad
+            const bool merge = !(p.dbg & 8) && (__popc(runs.heads) <= 24);
+            float* g0 = p.gpad[level0];
+            const int ntap = (p.filter == B200DR_FILTER_NEAREST) ? 1 : 4;
+            for (int t = 0; t < ntap; t++)
+            {
+                int tc = (t == 0) ? tc0.x : (t == 1) ? tc0.y : (t == 2) ? tc0.z : tc0.w;
+                float w = (t == 0) ? w0.x : (t == 1) ? w0.y : (t == 2) ? w0.z : w0.w;
+                float v[C];
+                #pragma unroll
+                for (int i = 0; i < C; i++) v[i] = act ? w * dy[i] : 0.f;
+                if (merge)
+                {
+                    #pragma unroll
+                    for (int i = 0; i < C; i++) v[i] = warp_run_sum_max4(v[i], runs);
+                    if (runs.is_head) scatter_tap<C>(g0, tc, 1.f, v);
+                }
+                else scatter_tap<C>(g0, tc, 1.f, v);
+            }
+            if (two)
+            {
+                float uv111 = uv1.x * uv1.y, uv110 = uv1.x - uv111, uv101 = uv1.y - uv111, uv100 = 1.f - uv1.x - uv101;
+                float* g1 = p.gpad[level1];
+                scatter_tap<C>(g1, tc1.x, uv100 * flevel, dy);
+                scatter_tap<C>(g1, tc1.y, uv110 * flevel, dy);
+                scatter_tap<C>(g1, tc1.z, uv101 * flevel, dy);
+                scatter_tap<C>(g1, tc1.w, uv111 * flevel, dy);
+            }
+        }
+
+        if (act && p.filter != B200DR_FILTER_NEAREST && !(p.dbg & 4))
+        {
+            const float* t0 = p.tex[level0];
+            float sclu0 = (float)lvl_w(p, level0), sclv0 = (float)lvl_h(p, level0);
+            float a00[C], a10[C], a01[C], a11[C];
+            unpack4<C>(texel4(t0, tc0.x, 4, 0), a00); unpack4<C>(texel4(t0, tc0.y, 4, 0), a10);
+            unpack4<C>(texel4(t0, tc0.z, 4, 0), a01); unpack4<C>(texel4(t0, tc0.w, 4, 0), a11);
+            #pragma unroll
+            for (int i = 0; i < C; i++)
+            {
+                float dy0 = f0 * dy[i];
+                float ad = (a11[i] + a00[i] - a10[i] - a01[i]);
+                gu += dy0 * ((a10[i] - a00[i]) + uv0.y * ad) * sclu0;
+                gv += dy0 * ((a01[i] - a00[i]) + uv0.x * ad) * sclv0;
+            }
+            if (two)
+            {
+                const float* t1 = p.tex[level1];
+                float sclu1 = (float)lvl_w(p, level1), sclv1 = (float)lvl_h(p, level1);
+                float b00[C], b10[C], b01[C], b11[C];
+                unpack4<C>(texel4(t1, tc1.x, 4, 0), b00); unpack4<C>(texel4(t1, tc1.y, 4, 0), b10);
+                unpack4<C>(texel4(t1, tc1.z, 4, 0), b01); unpack4<C>(texel4(t1, tc1.w, 4, 0), b11);
+                #pragma unroll
+                for (int i = 0; i < C; i++)
+                {
+                    float dy1 = flevel * dy[i];
+                    float bd = (b11[i] + b00[i] - b10[i] - b01[i]);
+                    gu += dy1 * ((b10[i] - b00[i]) + uv1.y * bd) * sclu1;
+                    gv += dy1 * ((b01[i] - b00[i]) + uv1.x * bd) * sclv1;
+                    float a = bilerp(a00[i], a10[i], a01[i], a11[i], uv0);
+                    float b = bilerp(b00[i], b10[i], b01[i], b11[i], uv1);
+                    df += (b - a) * dy[i];
+                }
+            }
+        }
+    }
+    if (inb)
+    {
+        if (p.g_uv) st_stream_f2((float2*)p.g_uv + pidx, make_float2(gu, gv));
+        if (p.g_bias) st_stream_f(p.g_bias + pidx, df);
+        if (p.g_uv_da) st_stream_f4((float4*)p.g_uv_da + pidx, make_float4(dw.x * df, dw.y * df, dw.z * df, dw.w * df));
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(TEXG_THREADS, 5) texture_grad_fast(const TexParams p)
 {
     constexpr int SK = (C == 3) ? 3 : 1;
-    __shared__ __align__(16) float s_stage[TEX_THREADS / 32][32 * SK];
+    __shared__ __align__(16) float s_stage[TEXG_THREADS / 32][32 * SK];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t hw = (size_t)p.H * p.W;
     const size_t total = hw * p.N;
     const size_t groups = (total + 31) >> 5;
-    const size_t wstride = (size_t)gridDim.x * (TEX_THREADS / 32);
+    const size_t wstride = (size_t)gridDim.x * (TEXG_THREADS / 32);
     const bool trilinear = (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
     Pending<C> pd;
     pd.key = -1; pd.u = 0; pd.v = 0; pd.level = 0; pd.tc = make_int4(-1, -1, -1, -1); pd.w = make_float4(0.f, 0.f, 0.f, 0.f);
     #pragma unroll
     for (int i = 0; i < C; i++) pd.sum[i] = 0.f;
 
-    for (size_t g = (size_t)blockIdx.x * (TEX_THREADS / 32) + warp; g < groups; g += wstride)
+    for (size_t g0 = (size_t)blockIdx.x * (TEXG_THREADS / 32) + warp; g0 < groups; g0 += TEXG_UNROLL * wstride)
     {
-        size_t pidx = g * 32 + lane;
-        bool inb = pidx < total;
-        bool full = (g * 32 + 32 <= total);
-        float dy[C];
+        TexGradIn<C> in[TEXG_UNROLL];
         #pragma unroll
-        for (int i = 0; i < C; i++) dy[i] = 0.f;
-        // every streaming load of the group is issued before the first use (dy decides `act`, but waiting for it before
-        // fetching uv / uv_da would serialise two DRAM round trips)
-        float2 uv = make_float2(0.f, 0.f); float4 da = make_float4(0.f, 0.f, 0.f, 0.f); float bias = 0.f;
-        if (inb)
-        {
-            uv = ld_stream_f2((const float2*)p.uv + pidx);
-            if (p.uv_da) da = ld_stream_f4((const float4*)p.uv_da + pidx);
-            if (p.bias) bias = ld_stream_f(p.bias + pidx);
-        }
-        warp_load_aos<C>(p.dy + g * 32 * C, dy, lane, inb, full, s_stage[warp]);
-        unsigned dmax = 0u;
+        for (int u = 0; u < TEXG_UNROLL; u++) texgrad_issue<C>(p, g0 + u * wstride, groups, total, lane, in[u]);
         #pragma unroll
-        for (int i = 0; i < C; i++) dmax |= __float_as_uint(dy[i]);
-        bool act = inb && (__uint_as_float(dmax) != 0.f);
-
-        float gu = 0.f, gv = 0.f, df = 0.f;
-        float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (__any_sync(0xffffffffu, act))
-        {
-            int level0 = 0, level1 = 0; float flevel = 0.f;
-            int4 tc0 = make_int4(-1, -1, -1, -1), tc1 = tc0;
-            float2 uv0 = make_float2(0.f, 0.f), uv1 = uv0;
-            bool two = false;
-            float f0 = 1.f;
-            if (act)
-            {
-                int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
-                if (p.filter == B200DR_FILTER_NEAREST) tc0.x = index_nearest(p, uv.x, uv.y, tz);
-                else
-                {
-                    mip_level_from<true>(p, da, bias, level0, level1, flevel, dw);
-                    uv0 = index_linear(p, uv.x, uv.y, tz, level0, tc0);
-                    two = trilinear && (flevel > 0.f);
-                    f0 = trilinear ? (1.f - flevel) : 1.f;
-                    if (two) uv1 = index_linear(p, uv.x, uv.y, tz, level1, tc1);
-                }
-            }
-            float uv011 = uv0.x * uv0.y, uv010 = uv0.x - uv011, uv001 = uv0.y - uv011, uv000 = 1.f - uv0.x - uv001;
-            float4 w0 = (p.filter == B200DR_FILTER_NEAREST) ? make_float4(1.f, 0.f, 0.f, 0.f)
-                                                            : make_float4(uv000 * f0, uv010 * f0, uv001 * f0, uv011 * f0);
-
-            // Whole warp on one texel quad with identical weights?  (shuffles first: no short-circuit around collectives)
-            int key0 = act ? (tc0.x ^ (level0 << 27)) : -1;
-            int k0 = __shfl_sync(0xffffffffu, key0, 0);
-            int u0 = __shfl_sync(0xffffffffu, __float_as_int(w0.y), 0);
-            int v0 = __shfl_sync(0xffffffffu, __float_as_int(w0.z), 0);
-            bool same = act && !two && (key0 == k0) && (__float_as_int(w0.y) == u0) && (__float_as_int(w0.z) == v0);
-            bool uniform = __all_sync(0xffffffffu, same);
-            if (uniform)
-            {
-                if (!(p.dbg & 2))
-                {
-                    if (pd.key != key0 || pd.u != u0 || pd.v != v0)
-                    {
-                        pending_flush<C>(pd, p, lane);
-                        pd.key = key0; pd.u = u0; pd.v = v0; pd.level = level0; pd.tc = tc0; pd.w = w0;
-                        #pragma unroll
-                        for (int i = 0; i < C; i++) pd.sum[i] = 0.f;
-                    }
-                    #pragma unroll
-                    for (int i = 0; i < C; i++) pd.sum[i] += warp_sum(dy[i]);
-                }
-            }
-            else if (!(p.dbg & 1))
-            {
-                // Neighbouring pixels of a magnified texture sit on the same texel quad: sum runs of up to 4 equal quads
-                // with two shuffle steps, so a quad receives one vector reduction per run instead of one per pixel
-                // (same-address reductions inside one instruction serialise).  Skipped when the warp has few duplicates.
-                WarpRuns runs = warp_runs_max4((act && !two && tc0.x >= 0 && tc0.w >= 0) ? key0 : -1 - lane, tc0.w);    // first and diagonal tap pin the whole quad
-                const bool merge = !(p.dbg & 8) && (__popc(runs.heads) <= 24);
-                float* g0 = p.gpad[level0];
-                const int ntap = (p.filter == B200DR_FILTER_NEAREST) ? 1 : 4;
-                for (int t = 0; t < ntap; t++)
-                {
-                    int tc = (t == 0) ? tc0.x : (t == 1) ? tc0.y : (t == 2) ? tc0.z : tc0.w;
-                    float w = (t == 0) ? w0.x : (t == 1) ? w0.y : (t == 2) ? w0.z : w0.w;
-                    float v[C];
-                    #pragma unroll
-                    for (int i = 0; i < C; i++) v[i] = act ? w * dy[i] : 0.f;
-                    if (merge)
-                    {
-                        #pragma unroll
-                        for (int i = 0; i < C; i++) v[i] = warp_run_sum_max4(v[i], runs);
-                        if (runs.is_head) scatter_tap<C>(g0, tc, 1.f, v);
-                    }
-                    else scatter_tap<C>(g0, tc, 1.f, v);
-                }
-                if (two)
-                {
-                    float uv111 = uv1.x * uv1.y, uv110 = uv1.x - uv111, uv101 = uv1.y - uv111, uv100 = 1.f - uv1.x - uv101;
-                    float* g1 = p.gpad[level1];
-                    scatter_tap<C>(g1, tc1.x, uv100 * flevel, dy);
-                    scatter_tap<C>(g1, tc1.y, uv110 * flevel, dy);
-                    scatter_tap<C>(g1, tc1.z, uv101 * flevel, dy);
-                    scatter_tap<C>(g1, tc1.w, uv111 * flevel, dy);
-                }
-            }
-
-            if (act && p.filter != B200DR_FILTER_NEAREST && !(p.dbg & 4))
-            {
-                const float* t0 = p.tex[level0];
-                float sclu0 = (float)lvl_w(p, level0), sclv0 = (float)lvl_h(p, level0);
-                float a00[C], a10[C], a01[C], a11[C];
-                unpack4<C>(texel4(t0, tc0.x, 4, 0), a00); unpack4<C>(texel4(t0, tc0.y, 4, 0), a10);
-                unpack4<C>(texel4(t0, tc0.z, 4, 0), a01); unpack4<C>(texel4(t0, tc0.w, 4, 0), a11);
-                #pragma unroll
-                for (int i = 0; i < C; i++)
-                {
-                    float dy0 = f0 * dy[i];
-                    float ad = (a11[i] + a00[i] - a10[i] - a01[i]);
-                    gu += dy0 * ((a10[i] - a00[i]) + uv0.y * ad) * sclu0;
-                    gv += dy0 * ((a01[i] - a00[i]) + uv0.x * ad) * sclv0;
-                }
-                if (two)
-                {
-                    const float* t1 = p.tex[level1];
-                    float sclu1 = (float)lvl_w(p, level1), sclv1 = (float)lvl_h(p, level1);
-                    float b00[C], b10[C], b01[C], b11[C];
-                    unpack4<C>(texel4(t1, tc1.x, 4, 0), b00); unpack4<C>(texel4(t1, tc1.y, 4, 0), b10);
-                    unpack4<C>(texel4(t1, tc1.z, 4, 0), b01); unpack4<C>(texel4(t1, tc1.w, 4, 0), b11);
-                    #pragma unroll
-                    for (int i = 0; i < C; i++)
-                    {
-                        float dy1 = flevel * dy[i];
-                        float bd = (b11[i] + b00[i] - b10[i] - b01[i]);
-                        gu += dy1 * ((b10[i] - b00[i]) + uv1.y * bd) * sclu1;
-                        gv += dy1 * ((b01[i] - b00[i]) + uv1.x * bd) * sclv1;
-                        float a = bilerp(a00[i], a10[i], a01[i], a11[i], uv0);
-                        float b = bilerp(b00[i], b10[i], b01[i], b11[i], uv1);
-                        df += (b - a) * dy[i];
-                    }
-                }
-            }
-        }
-        if (inb)
-        {
-            if (p.g_uv) st_stream_f2((float2*)p.g_uv + pidx, make_float2(gu, gv));
-            if (p.g_bias) st_stream_f(p.g_bias + pidx, df);
-            if (p.g_uv_da) st_stream_f4((float4*)p.g_uv_da + pidx, make_float4(dw.x * df, dw.y * df, dw.z * df, dw.w * df));
-        }
+        for (int u = 0; u < TEXG_UNROLL; u++)
+            if (in[u].g < groups) texgrad_group<C>(p, in[u], pd, lane, s_stage[warp], hw, trilinear);      // warp-uniform
     }
     pending_flush<C>(pd, p, lane);
 }
@@ -996,14 +1021,15 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
     if (C <= 4 && B200DR_ALIGNED16(dy))
     {
         size_t groups = ((size_t)N * H * W + 31) / 32;
-        size_t blocks = (groups + (TEX_THREADS / 32) - 1) / (TEX_THREADS / 32);
-        size_t bcap = (size_t)b200dr_num_sms() * 8;
+        size_t per_cta = (TEXG_THREADS / 32) * TEXG_UNROLL;
+        size_t blocks = (groups + per_cta - 1) / per_cta;
+        size_t bcap = (size_t)b200dr_num_sms() * 20;
         if (blocks > bcap) blocks = bcap;
         switch (C) {
-        case 1: texture_grad_fast<1><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
-        case 2: texture_grad_fast<2><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
-        case 3: texture_grad_fast<3><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
-        case 4: texture_grad_fast<4><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
+        case 1: texture_grad_fast<1><<<(unsigned)blocks, TEXG_THREADS, 0, stream>>>(p); break;
+        case 2: texture_grad_fast<2><<<(unsigned)blocks, TEXG_THREADS, 0, stream>>>(p); break;
+        case 3: texture_grad_fast<3><<<(unsigned)blocks, TEXG_THREADS, 0, stream>>>(p); break;
+        case 4: texture_grad_fast<4><<<(unsigned)blocks, TEXG_THREADS, 0, stream>>>(p); break;
         }
     }
     else
