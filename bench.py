@@ -34,6 +34,15 @@ from nvdiffrast_b200.distributed import allreduce_shared_grads  # noqa: E402
 FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
+def measured_traffic():
+    """DRAM bytes per pixel per op from the committed ncu --set full capture (profiles/r01_traffic.json), or {}."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -377,8 +386,10 @@ def main():
         dom = max((n for n in ops if n in nbytes), key=lambda n: ops[n][0])
         avg = ops[dom][0] / ops[dom][1]
         ach = nbytes[dom] / (avg * 1e-3) / 1e9
+        tr = measured_traffic().get(dom.replace("b200dr_", ""))
         out["roofline"] = {"kernel": dom.replace("b200dr_", ""), "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                           "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                           "frac": ach / peak, "traffic": (tr["dram_bytes_per_pixel"] * P if tr else None),
+                           "traffic_source": (tr.get("source") if tr else None), "peak_source": peak_src,
                            "algorithmic_bytes_per_launch": nbytes[dom], "avg_launch_ms": avg}
         chain_bytes = sum(nbytes[n] * ops[n][1] / K for n in ops if n in nbytes)
         out["chain_roofline"] = {"algorithmic_bytes_per_step": chain_bytes, "achieved_GBps": chain_bytes / (ms / K * 1e-3) / 1e9,

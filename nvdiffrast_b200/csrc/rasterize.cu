@@ -26,7 +26,9 @@ struct RastParams
     const float*    pos;
     const int32_t*  tri;
     const int32_t*  ranges;         // device [N,2] or NULL
-    int             N, V, T, H, W;
+    int             N, V, T, H, W;          // H, W: full output resolution
+    int             vpW, vpH, offX, offY;   // current viewport (<= 2048^2) inside the output; larger images are tiled
+    float           vxs, vxo, vys, vyo;     // clip-space remap into the viewport: x' = x*vxs + w*vxo (impl/RasterImpl.cpp:295-298)
     int             instance_mode;
     int             max_tris;       // per image
     int             cap;            // record slots per image (7 * max_tris)
@@ -234,6 +236,10 @@ static __device__ __forceinline__ bool fetch_triangle(const RastParams& p, int n
     if (i0 >= (uint32_t)p.V || i1 >= (uint32_t)p.V || i2 >= (uint32_t)p.V) return false;
     const float4* vb = (const float4*)p.pos + (p.instance_mode ? (size_t)n * p.V : 0);
     v0 = __ldg(vb + i0); v1 = __ldg(vb + i1); v2 = __ldg(vb + i2);
+    // viewport remap, mul + fma as in the reference build (impl/TriangleSetup.inl:262-267); identity for a single viewport
+    v0.x = __fmaf_rn(v0.x, p.vxs, __fmul_rn(v0.w, p.vxo)); v0.y = __fmaf_rn(v0.y, p.vys, __fmul_rn(v0.w, p.vyo));
+    v1.x = __fmaf_rn(v1.x, p.vxs, __fmul_rn(v1.w, p.vxo)); v1.y = __fmaf_rn(v1.y, p.vys, __fmul_rn(v1.w, p.vyo));
+    v2.x = __fmaf_rn(v2.x, p.vxs, __fmul_rn(v2.w, p.vxo)); v2.y = __fmaf_rn(v2.y, p.vys, __fmul_rn(v2.w, p.vyo));
     return true;
 }
 
@@ -348,7 +354,7 @@ static __device__ __forceinline__ void process_triangle(const RastParams& p, int
     SubTri s;
     if (cls == 1)
     {
-        if (snap_and_setup(v0, v1, v2, p.W, p.H, s)) emit(s);
+        if (snap_and_setup(v0, v1, v2, p.vpW, p.vpH, s)) emit(s);
         return;
     }
     // Rare: clip to the frustum, fan-triangulate from the first polygon vertex (impl/TriangleSetup.inl:355-434).
@@ -361,7 +367,7 @@ static __device__ __forceinline__ void process_triangle(const RastParams& p, int
     for (int i = 2; i < nv; i++)
     {
         float4 c2 = bary_point(v0, d1, d2, bary[i * 2 + 0], bary[i * 2 + 1]);
-        if (snap_and_setup(c0, c1, c2, p.W, p.H, s)) emit(s);
+        if (snap_and_setup(c0, c1, c2, p.vpW, p.vpH, s)) emit(s);
         c1 = c2;
     }
 }
@@ -407,7 +413,7 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
     const int tid = threadIdx.x;
     const int n = blockIdx.z;
     const int binX0 = blockIdx.x << BIN_LOG2, binY0 = blockIdx.y << BIN_LOG2;
-    const int binX1 = min(binX0 + BIN_SIZE, p.W) - 1, binY1 = min(binY0 + BIN_SIZE, p.H) - 1;
+    const int binX1 = min(binX0 + BIN_SIZE, p.vpW) - 1, binY1 = min(binY0 + BIN_SIZE, p.vpH) - 1;   // viewport-local pixels
 
     // Thread -> 4x4 pixel block.  A warp covers 32x16 pixels (8x4 blocks).
     const int lane = tid & 31, warp = tid >> 5;
@@ -422,8 +428,9 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
         #pragma unroll
         for (int j = 0; j < 4; j++)
         {
-            int Y = binY0 + ty + j, X = binX0 + tx;
-            if (Y < p.H && X + 3 < p.W && (p.W & 3) == 0)
+            int ly = binY0 + ty + j, lx = binX0 + tx;
+            int Y = p.offY + ly, X = p.offX + lx;
+            if (ly < p.vpH && lx + 3 < p.vpW && (p.W & 3) == 0 && (p.offX & 3) == 0)
             {
                 uint4 v = *(const uint4*)(p.peel_in + ((size_t)n * p.H + Y) * p.W + X);
                 peelD[j * 4 + 0] = v.x; peelD[j * 4 + 1] = v.y; peelD[j * 4 + 2] = v.z; peelD[j * 4 + 3] = v.w;
@@ -432,7 +439,7 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
             {
                 #pragma unroll
                 for (int i = 0; i < 4; i++)
-                    peelD[j * 4 + i] = (Y < p.H && X + i < p.W) ? p.peel_in[((size_t)n * p.H + Y) * p.W + X + i] : 0xFFFFFFFFu;
+                    peelD[j * 4 + i] = (ly < p.vpH && lx + i < p.vpW) ? p.peel_in[((size_t)n * p.H + Y) * p.W + X + i] : 0xFFFFFFFFu;
             }
         }
     }
@@ -471,9 +478,9 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
                 int x0 = (int)(bb.x & 0xFFFFu), x1 = (int)(bb.x >> 16), y0 = (int)(bb.y & 0xFFFFu), y1 = (int)(bb.y >> 16);
                 uint4 ra = __ldg(recs + i * 2), rb = __ldg(recs + i * 2 + 1);
                 int ax = s16lo(ra.x), ay = s16hi(ra.x), bx = s16lo(ra.y), by = s16hi(ra.y), cx = s16lo(ra.z), cy = s16hi(ra.z);
-                Edge e0 = make_edge(ax, ay, bx, by, binX0, binY0, p.W, p.H);
-                Edge e1 = make_edge(bx, by, cx, cy, binX0, binY0, p.W, p.H);
-                Edge e2 = make_edge(cx, cy, ax, ay, binX0, binY0, p.W, p.H);
+                Edge e0 = make_edge(ax, ay, bx, by, binX0, binY0, p.vpW, p.vpH);
+                Edge e1 = make_edge(bx, by, cx, cy, binX0, binY0, p.vpW, p.vpH);
+                Edge e2 = make_edge(cx, cy, ax, ay, binX0, binY0, p.vpW, p.vpH);
                 BinTri t;
                 t.e0c = e0.c; t.e0sx = e0.sx; t.e0sy = e0.sy;
                 t.e1c = e1.c; t.e1sx = e1.sx; t.e1sy = e1.sy;
@@ -542,15 +549,15 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
         #pragma unroll
         for (int j = 0; j < 4; j++)
         {
-            int Y = binY0 + ty + j, X = binX0 + tx;
-            if (Y >= p.H) continue;
-            uint32_t* dst = p.depth_out + ((size_t)n * p.H + Y) * p.W + X;
-            if (X + 3 < p.W && (p.W & 3) == 0)
+            int ly = binY0 + ty + j, lx = binX0 + tx;
+            if (ly >= p.vpH) continue;
+            uint32_t* dst = p.depth_out + ((size_t)n * p.H + p.offY + ly) * p.W + p.offX + lx;
+            if (lx + 3 < p.vpW && (p.W & 3) == 0 && (p.offX & 3) == 0)
                 *(uint4*)dst = make_uint4(bestD[j * 4 + 0], bestD[j * 4 + 1], bestD[j * 4 + 2], bestD[j * 4 + 3]);
             else
             {
                 #pragma unroll
-                for (int i = 0; i < 4; i++) if (X + i < p.W) dst[i] = bestD[j * 4 + i];
+                for (int i = 0; i < 4; i++) if (lx + i < p.vpW) dst[i] = bestD[j * 4 + i];
             }
         }
     }
@@ -565,8 +572,8 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
     {
         int q = tid + k * BIN_THREADS;
         int lx = q & (BIN_SIZE - 1), ly = q >> BIN_LOG2;
-        int X = binX0 + lx, Y = binY0 + ly;
-        if (X >= p.W || Y >= p.H) continue;
+        if (binX0 + lx >= p.vpW || binY0 + ly >= p.vpH) continue;
+        int X = p.offX + binX0 + lx, Y = p.offY + binY0 + ly;                   // output pixel
         float4 o = zero, db = zero;
         if (any)
         {
@@ -587,7 +594,7 @@ template <bool PEEL_IN>
 static __device__ __forceinline__ void scatter_fragment(const RastParams& p, int n, int X, int Y, uint32_t depth, uint32_t id)
 {
     if (depth > DR_DEPTH_MAX) return;
-    size_t pi = ((size_t)n * p.H + Y) * p.W + X;
+    size_t pi = ((size_t)n * p.H + p.offY + Y) * p.W + p.offX + X;    // X, Y are viewport-local
     if (PEEL_IN) { if (depth <= __ldg(p.peel_in + pi)) return; }
     unsigned long long key = ((unsigned long long)depth << 32) | (unsigned long long)(0xFFFFFFFFu - id);
     atomicMin(p.keys + pi, key);
@@ -602,9 +609,9 @@ struct ScatterEmit
     // warp-cooperative: lanes that hold a large sub-triangle publish it, the whole warp walks its bbox in 8x4 blocks
     __device__ __forceinline__ void walk_small(const SubTri& s)
     {
-        Edge e0 = make_edge(s.x0, s.y0, s.x1, s.y1, s.bx0, s.by0, p.W, p.H);
-        Edge e1 = make_edge(s.x1, s.y1, s.x2, s.y2, s.bx0, s.by0, p.W, p.H);
-        Edge e2 = make_edge(s.x2, s.y2, s.x0, s.y0, s.bx0, s.by0, p.W, p.H);
+        Edge e0 = make_edge(s.x0, s.y0, s.x1, s.y1, s.bx0, s.by0, p.vpW, p.vpH);
+        Edge e1 = make_edge(s.x1, s.y1, s.x2, s.y2, s.bx0, s.by0, p.vpW, p.vpH);
+        Edge e2 = make_edge(s.x2, s.y2, s.x0, s.y0, s.bx0, s.by0, p.vpW, p.vpH);
         uint32_t zr = s.zb + s.zx * (uint32_t)s.bx0 + s.zy * (uint32_t)s.by0;
         for (int Y = s.by0; Y <= s.by1; Y++)
         {
@@ -645,9 +652,9 @@ static __device__ __forceinline__ void scatter_subtri_warp(const RastParams& p, 
         int by0 = __shfl_sync(0xffffffffu, s.by0, src), by1 = __shfl_sync(0xffffffffu, s.by1, src);
         uint32_t tid_ = __shfl_sync(0xffffffffu, id, src);
         int lx = lane & 7, ly = lane >> 3;
-        Edge e0 = make_edge(x0, y0, x1, y1, bx0 + lx, by0 + ly, p.W, p.H);
-        Edge e1 = make_edge(x1, y1, x2, y2, bx0 + lx, by0 + ly, p.W, p.H);
-        Edge e2 = make_edge(x2, y2, x0, y0, bx0 + lx, by0 + ly, p.W, p.H);
+        Edge e0 = make_edge(x0, y0, x1, y1, bx0 + lx, by0 + ly, p.vpW, p.vpH);
+        Edge e1 = make_edge(x1, y1, x2, y2, bx0 + lx, by0 + ly, p.vpW, p.vpH);
+        Edge e2 = make_edge(x2, y2, x0, y0, bx0 + lx, by0 + ly, p.vpW, p.vpH);
         uint32_t zr = zb + zx * (uint32_t)(bx0 + lx) + zy * (uint32_t)(by0 + ly);
         for (int Y = by0 + ly; Y <= by1; Y += 4)
         {
@@ -680,7 +687,7 @@ __global__ void __launch_bounds__(128) raster_scatter_kernel(const RastParams p)
     // fast path: triangles fully inside the frustum
     {
         SubTri s;
-        bool valid = (cls == 1) && snap_and_setup(v0, v1, v2, p.W, p.H, s);
+        bool valid = (cls == 1) && snap_and_setup(v0, v1, v2, p.vpW, p.vpH, s);
         scatter_subtri_warp<PEEL_IN>(p, n, valid, s, id);
     }
     // rare path: clipped triangles, one fan triangle at a time (warp-uniform trip count)
@@ -707,7 +714,7 @@ __global__ void __launch_bounds__(128) raster_scatter_kernel(const RastParams p)
             if (i < nv)
             {
                 float4 c2 = bary_point(v0, d1, d2, bary[i * 2 + 0], bary[i * 2 + 1]);
-                valid = snap_and_setup(c0, c1, c2, p.W, p.H, s);
+                valid = snap_and_setup(c0, c1, c2, p.vpW, p.vpH, s);
                 c1 = c2;
             }
             scatter_subtri_warp<PEEL_IN>(p, n, valid, s, id);
@@ -948,7 +955,7 @@ extern "C" int b200dr_rasterize_fwd(const float* pos, const int32_t* tri, const 
     cudaStream_t stream = (cudaStream_t)stream_;
     B200DR_CHECK(N > 0 && V > 0 && T > 0, "rasterize_fwd(): pos/tri must be non-empty");
     B200DR_CHECK(H > 0 && W > 0, "rasterize_fwd(): resolution must be [>0, >0]");
-    B200DR_CHECK(H <= 2048 && W <= 2048, "rasterize_fwd(): resolution above 2048x2048 is not supported yet");
+    B200DR_CHECK(H <= 32768 && W <= 32768, "rasterize_fwd(): resolution too large");
     B200DR_CHECK(instance_mode || ranges_dev, "rasterize_fwd(): range mode requires ranges");
     B200DR_CHECK(max_tris > 0 && max_tris < (1 << 24), "rasterize_fwd(): triangle count per image must be in [1, 2^24)");
     B200DR_CHECK(B200DR_ALIGNED16(pos), "rasterize_fwd(): pos input tensor not aligned to float4");
@@ -958,6 +965,7 @@ extern "C" int b200dr_rasterize_fwd(const float* pos, const int32_t* tri, const 
     B200DR_CHECK(path == B200DR_RAST_BINS || path == B200DR_RAST_SCATTER, "rasterize_fwd(): invalid path");
     B200DR_CHECK(scratch && scratch_bytes >= b200dr_rasterize_scratch_bytes(N, max_tris, H, W, path), "rasterize_fwd(): scratch buffer too small");
     B200DR_CHECK(N <= 65535, "rasterize_fwd(): minibatch size above 65535 is not supported");
+    B200DR_CHECK(!peel_depth_in || depth_out, "rasterize_fwd(): peeling needs a depth output buffer");
 
     RastParams p = {};
     p.pos = pos; p.tri = tri; p.ranges = ranges_dev;
@@ -974,27 +982,51 @@ extern "C" int b200dr_rasterize_fwd(const float* pos, const int32_t* tri, const 
         p.extra = (int*)s;                    s += align_up((size_t)N * sizeof(int), 256);
         p.bbox = (uint2*)s;                   s += align_up((size_t)N * p.cap * sizeof(uint2), 256);
         p.rec = (uint4*)s;
-        cudaMemsetAsync(p.extra, 0, (size_t)N * sizeof(int), stream);
-        raster_setup_kernel<<<dim3((max_tris + 127) / 128, N), 128, 0, stream>>>(p);
-        B200DR_CHECK_LAUNCH("rasterize_fwd(setup)");
-        dim3 grid((W + BIN_SIZE - 1) / BIN_SIZE, (H + BIN_SIZE - 1) / BIN_SIZE, N);
-        if (peel_depth_in)
-        {
-            B200DR_CHECK(depth_out, "rasterize_fwd(): peeling needs a depth output buffer");
-            raster_bins_kernel<true, true><<<grid, BIN_THREADS, 0, stream>>>(p);
-        }
-        else if (depth_out) raster_bins_kernel<false, true><<<grid, BIN_THREADS, 0, stream>>>(p);
-        else                raster_bins_kernel<false, false><<<grid, BIN_THREADS, 0, stream>>>(p);
-        B200DR_CHECK_LAUNCH("rasterize_fwd(bins)");
     }
     else
     {
         p.keys = (unsigned long long*)scratch;
         cudaMemsetAsync(p.keys, 0xFF, (size_t)N * H * W * sizeof(unsigned long long), stream);
-        dim3 grid((max_tris + 127) / 128, N);
-        if (peel_depth_in) raster_scatter_kernel<true><<<grid, 128, 0, stream>>>(p);
-        else               raster_scatter_kernel<false><<<grid, 128, 0, stream>>>(p);
-        B200DR_CHECK_LAUNCH("rasterize_fwd(scatter)");
+    }
+
+    // Viewports larger than 2048 px are rendered as a grid of <= 2048^2 sub-viewports (the snapped coordinates are S16):
+    // same tiling and vertex remap as the reference (csrc/torch/torch_rasterize.cpp:98-124, impl/RasterImpl.cpp:295-298).
+    const int MAXVP = 2048;
+    int width8 = (W + 7) & ~7, height8 = (H + 7) & ~7;
+    int tileCountX = (width8 + MAXVP - 1) / MAXVP, tileCountY = (height8 + MAXVP - 1) / MAXVP;
+    int tileSizeX = (((width8 + tileCountX - 1) / tileCountX) + 7) & ~7;
+    int tileSizeY = (((height8 + tileCountY - 1) / tileCountY) + 7) & ~7;
+    for (int tileY = 0; tileY < tileCountY; tileY++)
+    for (int tileX = 0; tileX < tileCountX; tileX++)
+    {
+        p.offX = tileX * tileSizeX; p.offY = tileY * tileSizeY;
+        p.vpW = (W - p.offX) < tileSizeX ? (W - p.offX) : tileSizeX;
+        p.vpH = (H - p.offY) < tileSizeY ? (H - p.offY) : tileSizeY;
+        if (p.vpW <= 0 || p.vpH <= 0) continue;
+        p.vxs = (float)W / (float)p.vpW; p.vys = (float)H / (float)p.vpH;
+        p.vxo = (float)(W - p.vpW - 2 * p.offX) / (float)p.vpW;
+        p.vyo = (float)(H - p.vpH - 2 * p.offY) / (float)p.vpH;
+        if (path == B200DR_RAST_BINS)
+        {
+            cudaMemsetAsync(p.extra, 0, (size_t)N * sizeof(int), stream);
+            raster_setup_kernel<<<dim3((max_tris + 127) / 128, N), 128, 0, stream>>>(p);
+            B200DR_CHECK_LAUNCH("rasterize_fwd(setup)");
+            dim3 grid((p.vpW + BIN_SIZE - 1) / BIN_SIZE, (p.vpH + BIN_SIZE - 1) / BIN_SIZE, N);
+            if (peel_depth_in)  raster_bins_kernel<true, true><<<grid, BIN_THREADS, 0, stream>>>(p);
+            else if (depth_out) raster_bins_kernel<false, true><<<grid, BIN_THREADS, 0, stream>>>(p);
+            else                raster_bins_kernel<false, false><<<grid, BIN_THREADS, 0, stream>>>(p);
+            B200DR_CHECK_LAUNCH("rasterize_fwd(bins)");
+        }
+        else
+        {
+            dim3 grid((max_tris + 127) / 128, N);
+            if (peel_depth_in) raster_scatter_kernel<true><<<grid, 128, 0, stream>>>(p);
+            else               raster_scatter_kernel<false><<<grid, 128, 0, stream>>>(p);
+            B200DR_CHECK_LAUNCH("rasterize_fwd(scatter)");
+        }
+    }
+    if (path == B200DR_RAST_SCATTER)
+    {
         size_t total = (size_t)N * H * W;
         int blocks = (int)((total + 255) / 256);
         int maxb = b200dr_num_sms() * 16;

@@ -91,6 +91,22 @@ def test_rasterize_paths_identical(dr, ctx, name):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
+@pytest.mark.parametrize("res", [(2100, 2304), (1000, 4100)])
+def test_rasterize_tiled_viewports(dr, ctx, res):
+    """Resolutions above 2048 are rendered as a grid of sub-viewports with the reference's vertex remap
+    (csrc/torch/torch_rasterize.cpp:98-124): ids must match the oracle (and the reference when present) exactly."""
+    pos, tri = wl.soup_scene(1, 80, 4, size=0.7)
+    o = oracle.rasterize_fwd(pos, tri, res)
+    for path in (1, 2):
+        rast, db = run_rasterize(dr, ctx, pos, tri, res, path)
+        assert np.array_equal(rast[..., 3].astype(np.int64), o["tri_id"]), "path %d" % path
+    ref = load_reference()
+    if ref is not None:
+        rr, _ = ref.rasterize(ref.RasterizeCudaContext(), cu(pos), cu(tri), res)
+        assert np.array_equal(rast[..., 3], rr[..., 3].cpu().numpy())
+        assert_close(rast[..., :3], rr[..., :3].cpu().numpy(), 1e-6, 1e-5, "uvz vs ref (tiled)", max_bad_frac=1e-4)
+
+
 def test_rasterize_range_mode(dr, ctx):
     pos, tri, res = SCENES["soup"]()
     pos2d = np.ascontiguousarray(pos[0])
