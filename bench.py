@@ -178,6 +178,8 @@ class Pipeline:
         verts = self.dev["verts"].detach().requires_grad_(True)
         pos = torch.matmul(verts[None], self.dev["mvp"].transpose(1, 2)).contiguous()      # [n, V, 4] clip space
         rast, db = mod.rasterize(self.ctx, pos, self.tri, self.res)
+        if os.environ.get("BENCH_DEBUG"):
+            sys.stderr.write("coverage %.4f\n" % float((rast[..., 3] > 0).float().mean()))
         if self.workload == "c3":
             texc, texd = mod.interpolate(self.dev["uv"][None], rast, self.uv_idx, rast_db=db, diff_attrs="all")
             color = mod.texture(self.dev["tex"], texc, texd, filter_mode="linear-mipmap-linear", max_mip_level=9)

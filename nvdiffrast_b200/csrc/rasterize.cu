@@ -465,6 +465,7 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
         }
         __syncthreads();
         const int nidx = s_count;
+        __syncthreads();                                        // every thread has read the count before the next segment resets it
         if (nidx > 0) any = true;
 
         // ---- rasterize this bin's triangles, BIN_LIST at a time
