@@ -279,6 +279,9 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's banner / debug text on stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         torch.distributed.init_process_group("nccl", device_id=device)
 
     pipe = Pipeline(mod, args.workload, n_img, res, device, seed=rank)
