@@ -298,6 +298,62 @@ def test_texture_mip_stack_and_wrapper(dr):
     assert all(l.grad is not None and float(l.grad.abs().sum()) > 0 for l in levels)
 
 
+@pytest.mark.parametrize("res", [(1, 1), (3, 5), (8, 31), (65, 33)])
+def test_tiny_and_ragged_resolutions(dr, ctx, res):
+    pos, tri, _ = SCENES["soup"]()
+    o = oracle.rasterize_fwd(pos, tri, res)
+    for path in (1, 2):
+        rast, db = run_rasterize(dr, ctx, pos, tri, res, path)
+        assert np.array_equal(rast[..., 3].astype(np.int64), o["tri_id"])
+    attr = _rand_like((pos.shape[0], pos.shape[1], 3), 20)
+    trast = cu(o["rast"])
+    out, out_da = dr.interpolate(cu(attr), trast, cu(tri), rast_db=cu(o["rast_db"]), diff_attrs="all")
+    oo, oda = oracle.interpolate_fwd(attr, o["rast"], tri, o["rast_db"], "all")
+    assert_close(out.cpu().numpy(), oo, 1e-5, 1e-5, "out"); assert_close(out_da.cpu().numpy(), oda, 1e-5, 1e-4, "out_da")
+    color = np.random.default_rng(21).uniform(size=o["rast"].shape[:3] + (3,)).astype(np.float32)
+    aa = dr.antialias(cu(color), trast, cu(pos), cu(tri))
+    oaa, _ = oracle.antialias_fwd(color, o["rast"], pos, tri)
+    assert_close(aa.cpu().numpy(), oaa, 1e-5, 1e-4, "aa", max_bad_frac=2e-2)
+
+
+@pytest.mark.parametrize("A,diff", [(5, "all"), (12, [0, 11, -2]), (40, None), (40, "all")])
+def test_interpolate_generic_channel_counts(dr, ctx, A, diff):
+    """Channel counts outside the templated fast path (A > 4, attribute lists) use the staged generic kernels."""
+    pos, tri, res = SCENES["sphere"]()
+    rast, db = dr.rasterize(ctx, cu(pos), cu(tri), res)
+    rast_np, db_np = rast.cpu().numpy(), db.cpu().numpy()
+    attr = _rand_like((1, pos.shape[1], A), 22)
+    tattr = cu(attr).requires_grad_(True)
+    out, out_da = dr.interpolate(tattr, rast, cu(tri), rast_db=db if diff else None, diff_attrs=diff)
+    oo, oda = oracle.interpolate_fwd(attr, rast_np, tri, db_np if diff else None, diff)
+    assert_close(out.detach().cpu().numpy(), oo, 1e-5, 1e-5, "out")
+    if diff:
+        assert_close(out_da.detach().cpu().numpy(), oda, 1e-5, 1e-4, "out_da")
+    dy = _rand_like(out.shape, 23); dda = _rand_like(out_da.shape, 24)
+    ((out * cu(dy)).sum() + ((out_da * cu(dda)).sum() if diff else 0.0)).backward()
+    ga, _, _ = oracle.interpolate_grad(attr, rast_np, tri, dy, db_np if diff else None, dda if diff else None, diff)
+    assert_grad_close(tattr.grad.cpu().numpy(), ga, 2e-4, "g_attr")
+
+
+@pytest.mark.parametrize("C", [5, 8])
+@pytest.mark.parametrize("filter_mode", ["linear", "linear-mipmap-linear"])
+def test_texture_generic_channel_counts(dr, C, filter_mode):
+    """More than 4 channels: generic kernels (several 128-bit words per texel)."""
+    rng = np.random.default_rng(25)
+    tex = rng.uniform(size=(1, 16, 32, C)).astype(np.float32)
+    uv = rng.uniform(-0.2, 1.2, size=(1, 33, 47, 2)).astype(np.float32)
+    bias = rng.uniform(0, 3, size=(1, 33, 47)).astype(np.float32) if "mipmap" in filter_mode else None
+    ttex = cu(tex).requires_grad_(True); tuv = cu(uv).requires_grad_(True)
+    out = dr.texture(ttex, tuv, mip_level_bias=cu(bias) if bias is not None else None, filter_mode=filter_mode)
+    oo = oracle.texture_fwd(tex, uv, None, bias, filter_mode=filter_mode)
+    assert_close(out.detach().cpu().numpy(), oo, 2e-5, 1e-4, "tex out", max_bad_frac=2e-3)
+    dy = _rand_like(out.shape, 26)
+    (out * cu(dy)).sum().backward()
+    g = oracle.texture_grad(tex, uv, dy, None, bias, filter_mode=filter_mode)
+    assert_grad_close(ttex.grad.cpu().numpy(), g["g_tex"], 2e-3, "g_tex")
+    assert_close(tuv.grad.cpu().numpy(), g["g_uv"], 1e-3, 1e-3, "g_uv", max_bad_frac=5e-3)
+
+
 def test_error_behaviour(dr, ctx):
     pos, tri, res = SCENES["triangle"]()
     with pytest.raises(RuntimeError):
