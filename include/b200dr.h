@@ -121,7 +121,11 @@ int b200dr_antialias_grad(const float* color, const float* rast, const float* po
                           int N, int H, int W, int C, int V, int T, int instance_mode,
                           float* g_color, float* g_pos, void* stream);
 
-/* ---- texture (2-D) --------------------------------------------------------------------- */
+/* ---- texture (2-D and cube maps) -------------------------------------------------------- */
+/* Cube maps (boundary_mode B200DR_BOUNDARY_CUBE, texture_kernel.cu:31-317): tex is [texD,6,texW,texW,Cp], every mip level
+ * likewise; the six faces of a level are separate 2-D slices, so b200dr_texture_mip_info / _construct_mip /
+ * _grad_scratch_bytes / _pad are called with depth 6*texD, while b200dr_texture_fwd / _grad take texD itself (the
+ * minibatch), uv [N,H,W,3] direction vectors, uv_da / g_uv_da [N,H,W,6] (8-byte aligned).  At most 4 channels. */
 /* Texels are consumed from a CHANNEL-PADDED pyramid: every level (0 = base texture .. max_level) holds
  * Cp = (C + 3) & ~3 floats per texel, so a bilinear tap is one 128-bit load per corner.  The caller pads level 0 with
  * b200dr_texture_pad (when C % 4 != 0) and builds or pads the mip levels; all level pointers are 16-byte aligned. */
@@ -139,7 +143,7 @@ int b200dr_texture_pad(const float* src, float* dst, long long ntexels, int C, v
 int b200dr_texture_construct_mip(const float* tex, float* mip, int texW, int texH, int texD, int C,
                                  const int* offsets, int max_level, void* stream);
 
-/* Replaces texture_fwd / texture_fwd_mip (torch_texture.cpp:174-416, texture_kernel.cu:709-800), 2-D modes.
+/* Replaces texture_fwd / texture_fwd_mip (torch_texture.cpp:174-416, texture_kernel.cu:709-800).
  *   tex = padded level 0; mip_ptrs[1..max_level] = padded mip levels (mip_ptrs[0] ignored); C = real channel count. */
 int b200dr_texture_fwd(const float* tex, const float* const* mip_ptrs, int max_level,
                        const float* uv, const float* uv_da, const float* mip_level_bias,
@@ -147,7 +151,7 @@ int b200dr_texture_fwd(const float* tex, const float* const* mip_ptrs, int max_l
                        int filter_mode, int boundary_mode, float* out, void* stream);
 
 /* Replaces texture_grad_{nearest,linear,linear_mipmap_nearest,linear_mipmap_linear}
- * (torch_texture.cpp:421-716, texture_kernel.cu:843-1154), 2-D modes.
+ * (torch_texture.cpp:421-716, texture_kernel.cu:843-1154).
  *   scratch: b200dr_texture_grad_scratch_bytes() bytes (channel-padded gradient pyramid, zeroed here).
  *   tex / mip_ptrs: padded levels as in b200dr_texture_fwd.  g_tex (UNPADDED, shape of the user's tex) is fully written.  pull_mips != 0 (internal mip stack): mip-level gradients are pulled
  *   down into g_tex and g_mip_ptrs is ignored; pull_mips == 0 with max_level > 0 (custom mip stack): level l's

@@ -797,6 +797,345 @@ __global__ void __launch_bounds__(TEXG_THREADS, 5) texture_grad_fast(const TexPa
     pending_flush<C>(pd, p, lane);
 }
 
+// ================================================================================================
+// Cube maps (csrc/common/texture_kernel.cu:31-317, boundary_mode 'cube'): tex [D,6,w,w,C], uv = 3-D directions,
+// uv_da = d(direction)/d(X,Y) as three (dX,dY) pairs.  Separate, simple kernels (one pixel per thread, C <= 4 through the
+// padded pyramid); cube-face slices are addressed as depth 6*tz + face.  Face geometry is one table of (major, s, t axes
+// and signs) and the seam / corner handling is derived geometrically: the texel one step outside a face is projected onto
+// the neighbouring face in exact integer arithmetic (the reference uses two lookup tables, texture_kernel.cu:31-92).
+// ================================================================================================
+
+struct CubeFace { int M, S, T; float ss, st; };
+
+static __device__ __forceinline__ CubeFace cube_face(int idx)
+{
+    CubeFace f;
+    f.M = idx >> 1;
+    f.S = (f.M == 0) ? 2 : 0;
+    f.T = (f.M == 1) ? 2 : 1;
+    f.ss = (idx == 0 || idx == 5) ? -1.f : 1.f;
+    f.st = (idx == 2) ? 1.f : -1.f;
+    return f;
+}
+static __device__ __forceinline__ float comp3(float3 v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+static __device__ __forceinline__ void set3(float3& v, int a, float x) { if (a == 0) v.x = x; else if (a == 1) v.y = x; else v.z = x; }
+
+static __device__ __forceinline__ int cube_face_of(float3 v)
+{
+    float ax = fabsf(v.x), ay = fabsf(v.y), az = fabsf(v.z);
+    int idx; float c;
+    if (az > fmaxf(ax, ay)) { idx = 4; c = v.z; }
+    else if (ay > ax)       { idx = 2; c = v.y; }
+    else                    { idx = 0; c = v.x; }
+    if (c < 0.f) idx += 1;
+    return idx;
+}
+
+// direction -> face (or -1 for an invalid direction) and (s,t) in [0,1]
+static __device__ __forceinline__ int cube_st(float3 v, float& s, float& t)
+{
+    int idx = cube_face_of(v);
+    CubeFace f = cube_face(idx);
+    float m = __frcp_rz(fabsf(comp3(v, f.M))) * .5f;
+    float x = __fadd_rn(__fmul_rn(comp3(v, f.S), f.ss * m), .5f);
+    float y = __fadd_rn(__fmul_rn(comp3(v, f.T), f.st * m), .5f);
+    if (!isfinite(x) || !isfinite(y)) return -1;
+    s = fminf(fmaxf(x, 0.f), 1.f);
+    t = fminf(fmaxf(y, 0.f), 1.f);
+    return idx;
+}
+
+// texel (ix,iy) of face f, possibly one step outside it: linear index x + w*(y + w*face) on the proper face, -1 at a corner
+static __device__ __forceinline__ int cube_texel(int f, int ix, int iy, int w)
+{
+    bool xo = (ix < 0 || ix >= w), yo = (iy < 0 || iy >= w);
+    if (!xo && !yo) return ix + w * (iy + w * f);
+    if (xo && yo) return -1;
+    int a = 2 * ix + 1 - w, b = 2 * iy + 1 - w;
+    int dx, dy, dz;
+    switch (f) {
+    case 0: dx =  w; dy = -b; dz = -a; break;
+    case 1: dx = -w; dy = -b; dz =  a; break;
+    case 2: dx =  a; dy =  w; dz =  b; break;
+    case 3: dx =  a; dy = -w; dz = -b; break;
+    case 4: dx =  a; dy = -b; dz =  w; break;
+    default: dx = -a; dy = -b; dz = -w; break;
+    }
+    int M = (abs(dx) > w) ? 0 : (abs(dy) > w) ? 1 : 2;
+    int dM = (M == 0) ? dx : (M == 1) ? dy : dz;
+    int f2 = 2 * M + (dM < 0 ? 1 : 0);
+    int a2, b2;
+    switch (f2) {
+    case 0: a2 = -dz; b2 = -dy; break;
+    case 1: a2 =  dz; b2 = -dy; break;
+    case 2: a2 =  dx; b2 =  dz; break;
+    case 3: a2 =  dx; b2 = -dz; break;
+    case 4: a2 =  dx; b2 = -dy; break;
+    default: a2 = -dx; b2 = -dy; break;
+    }
+    int x2 = (abs(a2) >= w) ? (a2 > 0 ? w - 1 : 0) : ((a2 + w - 1) >> 1);
+    int y2 = (abs(b2) >= w) ? (b2 > 0 ? w - 1 : 0) : ((b2 + w - 1) >> 1);
+    return x2 + w * (y2 + w * f2);
+}
+
+// J^T (gu, gv): gradient w.r.t. the direction from the gradient w.r.t. (s,t)
+static __device__ __forceinline__ float3 cube_grad(float3 v, float gu, float gv)
+{
+    CubeFace f = cube_face(cube_face_of(v));
+    float c = comp3(v, f.M);
+    float m = __frcp_rz(fabsf(c));
+    float c0 = gu * comp3(v, f.S) * f.ss, c1 = gv * comp3(v, f.T) * f.st;
+    float gl = -(c0 + c1) * m * (c < 0.f ? -1.f : 1.f);
+    float3 r;
+    set3(r, f.S, gu * f.ss); set3(r, f.T, gv * f.st); set3(r, f.M, gl);
+    float h = m * .5f;
+    r.x *= h; r.y *= h; r.z *= h;
+    if (!isfinite(r.x) || !isfinite(r.y) || !isfinite(r.z)) return make_float3(0.f, 0.f, 0.f);
+    return r;
+}
+
+// (ds/dX, ds/dY, dt/dX, dt/dY) from d(direction)/d(X,Y)
+static __device__ __forceinline__ float4 cube_grad_st(float3 v, float3 dX, float3 dY)
+{
+    CubeFace f = cube_face(cube_face_of(v));
+    float c = comp3(v, f.M);
+    float m = __frcp_rz(fabsf(c));
+    float dm = m * .5f;
+    float sg = (c < 0.f) ? -1.f : 1.f;
+    float ku = -f.ss * comp3(v, f.S) * m * dm * sg;
+    float kv = -f.st * comp3(v, f.T) * m * dm * sg;
+    float4 r = make_float4(f.ss * dm * comp3(dX, f.S) + ku * comp3(dX, f.M), f.ss * dm * comp3(dY, f.S) + ku * comp3(dY, f.M),
+                           f.st * dm * comp3(dX, f.T) + kv * comp3(dX, f.M), f.st * dm * comp3(dY, f.T) + kv * comp3(dY, f.M));
+    if (!isfinite(r.x) || !isfinite(r.y) || !isfinite(r.z) || !isfinite(r.w)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    return r;
+}
+
+// d(ds/dX, ds/dY, dt/dX, dt/dY)/d(direction) contracted with dfdw
+static __device__ __forceinline__ float3 cube_grad2_dot(float3 v, float3 dX, float3 dY, float4 w)
+{
+    CubeFace f = cube_face(cube_face_of(v));
+    float c = comp3(v, f.M);
+    float ic = 1.f / c;
+    float h = .5f * fabsf(ic);
+    float vS = comp3(v, f.S), vT = comp3(v, f.T);
+    float oS = 0.f, oT = 0.f, oM = 0.f;
+    {
+        float SX = comp3(dX, f.S), TX = comp3(dX, f.T), cX = comp3(dX, f.M);
+        oS += w.x * (-f.ss * h * cX * ic); oT += w.z * (-f.st * h * cX * ic);
+        oM += w.x * (f.ss * h * ic * (-SX + 2.f * vS * cX * ic)) + w.z * (f.st * h * ic * (-TX + 2.f * vT * cX * ic));
+    }
+    {
+        float SX = comp3(dY, f.S), TX = comp3(dY, f.T), cX = comp3(dY, f.M);
+        oS += w.y * (-f.ss * h * cX * ic); oT += w.w * (-f.st * h * cX * ic);
+        oM += w.y * (f.ss * h * ic * (-SX + 2.f * vS * cX * ic)) + w.w * (f.st * h * ic * (-TX + 2.f * vT * cX * ic));
+    }
+    float3 r;
+    set3(r, f.S, oS); set3(r, f.T, oT); set3(r, f.M, oM);
+    return r;
+}
+
+// bilinear footprint on a cube level: 4 texel indices (neighbouring faces across seams, -1 missing), weights, corner flag
+static __device__ __forceinline__ float2 cube_index_linear(const TexParams& p, float3 v, int tz, int level, int4& tc, bool& corner)
+{
+    int w = lvl_w(p, level);
+    float s, t;
+    int face = cube_st(v, s, t);
+    if (face < 0) { tc = make_int4(-1, -1, -1, -1); corner = true; return make_float2(0.f, 0.f); }
+    float u = s * (float)w - 0.5f, vv = t * (float)w - 0.5f;
+    int iu0 = __float2int_rd(u), iv0 = __float2int_rd(vv);
+    u -= (float)iu0; vv -= (float)iv0;
+    int base = 6 * tz * w * w;
+    int q0 = cube_texel(face, iu0, iv0, w), q1 = cube_texel(face, iu0 + 1, iv0, w), q2 = cube_texel(face, iu0, iv0 + 1, w), q3 = cube_texel(face, iu0 + 1, iv0 + 1, w);
+    // Parity with the reference (texture_kernel.cu:87-91, 430-435): the missing corner texel is texel (0,0) of "face -1"
+    // (index -w*w) before the minibatch offset is added, so only tz == 0 sees a negative index (and the corner rule); for
+    // tz > 0 the tap lands on texel (0,0) of the previous item's -z face.
+    const int miss = -w * w;
+    tc = make_int4((q0 < 0 ? miss : q0) + base, (q1 < 0 ? miss : q1) + base, (q2 < 0 ? miss : q2) + base, (q3 < 0 ? miss : q3) + base);
+    corner = (tc.x | tc.y | tc.z | tc.w) < 0;
+    return make_float2(u, vv);
+}
+
+// four taps with the corner rule: the missing texel is the average of the other three (texture_kernel.cu:590-612)
+static __device__ __forceinline__ void cube_fetch(const float* t, int4 tc, bool corner, float4& a, float4& b, float4& c, float4& d)
+{
+    a = texel4(t, tc.x, 4, 0); b = texel4(t, tc.y, 4, 0); c = texel4(t, tc.z, 4, 0); d = texel4(t, tc.w, 4, 0);
+    if (corner)
+    {
+        float4 avg = make_float4((a.x + b.x + c.x + d.x) * 0.33333333f, (a.y + b.y + c.y + d.y) * 0.33333333f,
+                                 (a.z + b.z + c.z + d.z) * 0.33333333f, (a.w + b.w + c.w + d.w) * 0.33333333f);
+        if (tc.x < 0) a = avg;
+        if (tc.y < 0) b = avg;
+        if (tc.z < 0) c = avg;
+        if (tc.w < 0) d = avg;
+    }
+}
+
+// scatter weights with the corner rule: the missing tap's weight is shared by the other three (texture_kernel.cu:614-639)
+static __device__ __forceinline__ float4 cube_weights(float4 w, int4 tc, bool corner)
+{
+    if (!corner) return w;
+    float wm = (tc.x < 0 ? w.x : 0.f) + (tc.y < 0 ? w.y : 0.f) + (tc.z < 0 ? w.z : 0.f) + (tc.w < 0 ? w.w : 0.f);
+    wm *= 0.33333333f;
+    return make_float4(w.x + wm, w.y + wm, w.z + wm, w.w + wm);
+}
+
+static __device__ __forceinline__ int cube_nearest(const TexParams& p, float3 v, int tz)
+{
+    float s, t;
+    int face = cube_st(v, s, t);
+    if (face < 0) return -1;
+    int w = p.texW;
+    int iu = min(max(__float2int_rd(s * (float)w), 0), w - 1), iv = min(max(__float2int_rd(t * (float)w), 0), w - 1);
+    return iu + w * (iv + (6 * tz + face) * w);
+}
+
+static __device__ __forceinline__ void cube_load_dirs(const TexParams& p, size_t pidx, float3& v, float3& dX, float3& dY)
+{
+    const float* q = p.uv + pidx * 3;
+    v = make_float3(ld_stream_f(q), ld_stream_f(q + 1), ld_stream_f(q + 2));
+    dX = dY = make_float3(0.f, 0.f, 0.f);
+    if (p.uv_da)
+    {
+        const float2* d = (const float2*)p.uv_da + pidx * 3;
+        float2 d0 = ld_stream_f2(d), d1 = ld_stream_f2(d + 1), d2 = ld_stream_f2(d + 2);
+        dX = make_float3(d0.x, d1.x, d2.x); dY = make_float3(d0.y, d1.y, d2.y);
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) texture_cube_fwd_kernel(const TexParams p)
+{
+    const size_t hw = (size_t)p.H * p.W, total = hw * p.N;
+    for (size_t pidx = (size_t)blockIdx.x * 256 + threadIdx.x; pidx < total; pidx += (size_t)gridDim.x * 256)
+    {
+        int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
+        float3 v, dX, dY;
+        cube_load_dirs(p, pidx, v, dX, dY);
+        float o[C];
+        if (p.filter == B200DR_FILTER_NEAREST) unpack4<C>(texel4(p.tex[0], cube_nearest(p, v, tz), 4, 0), o);
+        else
+        {
+            int level0, level1; float flevel; float4 dw;
+            float bias = p.bias ? ld_stream_f(p.bias + pidx) : 0.f;
+            mip_level_from<false>(p, cube_grad_st(v, dX, dY), bias, level0, level1, flevel, dw);
+            int4 tc0; bool cor0;
+            float2 uv0 = cube_index_linear(p, v, tz, level0, tc0, cor0);
+            float4 a, b, c, d;
+            cube_fetch(p.tex[level0], tc0, cor0, a, b, c, d);
+            float4 r = bilerp4(a, b, c, d, uv0);
+            if (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && flevel > 0.f)
+            {
+                int4 tc1; bool cor1;
+                float2 uv1 = cube_index_linear(p, v, tz, level1, tc1, cor1);
+                cube_fetch(p.tex[level1], tc1, cor1, a, b, c, d);
+                float4 r1 = bilerp4(a, b, c, d, uv1);
+                r = make_float4(lerpf(r.x, r1.x, flevel), lerpf(r.y, r1.y, flevel), lerpf(r.z, r1.z, flevel), lerpf(r.w, r1.w, flevel));
+            }
+            unpack4<C>(r, o);
+        }
+        #pragma unroll
+        for (int i = 0; i < C; i++) p.out[pidx * C + i] = o[i];
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) texture_cube_grad_kernel(const TexParams p)
+{
+    const size_t hw = (size_t)p.H * p.W, total = hw * p.N;
+    const bool trilinear = (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
+    for (size_t pidx = (size_t)blockIdx.x * 256 + threadIdx.x; pidx < total; pidx += (size_t)gridDim.x * 256)
+    {
+        float dy[C];
+        unsigned dmax = 0u;
+        #pragma unroll
+        for (int i = 0; i < C; i++) { dy[i] = p.dy[pidx * C + i]; dmax |= __float_as_uint(dy[i]); }
+        float3 g_v = make_float3(0.f, 0.f, 0.f), g0 = g_v, g1 = g_v;
+        float df = 0.f;
+        if (__uint_as_float(dmax) != 0.f)
+        {
+            int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
+            float3 v, dX, dY;
+            cube_load_dirs(p, pidx, v, dX, dY);
+            if (p.filter == B200DR_FILTER_NEAREST) scatter_tap<C>(p.gpad[0], cube_nearest(p, v, tz), 1.f, dy);
+            else
+            {
+                int level0, level1; float flevel; float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
+                float bias = p.bias ? ld_stream_f(p.bias + pidx) : 0.f;
+                mip_level_from<true>(p, cube_grad_st(v, dX, dY), bias, level0, level1, flevel, dw);
+                float3 dfdv = make_float3(0.f, 0.f, 0.f);
+                if (trilinear && p.uv_da)
+                {
+                    dfdv = cube_grad2_dot(v, dX, dY, dw);
+                    if (!isfinite(dfdv.x) || !isfinite(dfdv.y) || !isfinite(dfdv.z)) { dfdv = make_float3(0.f, 0.f, 0.f); dw = make_float4(0.f, 0.f, 0.f, 0.f); }
+                }
+                bool two = trilinear && (flevel > 0.f);
+                float f0 = trilinear ? (1.f - flevel) : 1.f;
+                float gu = 0.f, gv = 0.f;
+                int4 tc0; bool cor0;
+                float2 uv0 = cube_index_linear(p, v, tz, level0, tc0, cor0);
+                {
+                    float uv011 = uv0.x * uv0.y, uv010 = uv0.x - uv011, uv001 = uv0.y - uv011, uv000 = 1.f - uv0.x - uv001;
+                    float4 w = cube_weights(make_float4(uv000 * f0, uv010 * f0, uv001 * f0, uv011 * f0), tc0, cor0);
+                    float* gp = p.gpad[level0];
+                    scatter_tap<C>(gp, tc0.x, w.x, dy); scatter_tap<C>(gp, tc0.y, w.y, dy);
+                    scatter_tap<C>(gp, tc0.z, w.z, dy); scatter_tap<C>(gp, tc0.w, w.w, dy);
+                }
+                float4 A00, A10, A01, A11;
+                cube_fetch(p.tex[level0], tc0, cor0, A00, A10, A01, A11);
+                float a00[C], a10[C], a01[C], a11[C];
+                unpack4<C>(A00, a00); unpack4<C>(A10, a10); unpack4<C>(A01, a01); unpack4<C>(A11, a11);
+                float sclu0 = (float)lvl_w(p, level0);
+                #pragma unroll
+                for (int i = 0; i < C; i++)
+                {
+                    float dy0 = f0 * dy[i];
+                    float ad = (a11[i] + a00[i] - a10[i] - a01[i]);
+                    gu += dy0 * ((a10[i] - a00[i]) + uv0.y * ad) * sclu0;
+                    gv += dy0 * ((a01[i] - a00[i]) + uv0.x * ad) * sclu0;
+                }
+                if (two)
+                {
+                    int4 tc1; bool cor1;
+                    float2 uv1 = cube_index_linear(p, v, tz, level1, tc1, cor1);
+                    float uv111 = uv1.x * uv1.y, uv110 = uv1.x - uv111, uv101 = uv1.y - uv111, uv100 = 1.f - uv1.x - uv101;
+                    float4 w = cube_weights(make_float4(uv100 * flevel, uv110 * flevel, uv101 * flevel, uv111 * flevel), tc1, cor1);
+                    float* gp = p.gpad[level1];
+                    scatter_tap<C>(gp, tc1.x, w.x, dy); scatter_tap<C>(gp, tc1.y, w.y, dy);
+                    scatter_tap<C>(gp, tc1.z, w.z, dy); scatter_tap<C>(gp, tc1.w, w.w, dy);
+                    float4 B00, B10, B01, B11;
+                    cube_fetch(p.tex[level1], tc1, cor1, B00, B10, B01, B11);
+                    float b00[C], b10[C], b01[C], b11[C];
+                    unpack4<C>(B00, b00); unpack4<C>(B10, b10); unpack4<C>(B01, b01); unpack4<C>(B11, b11);
+                    float sclu1 = (float)lvl_w(p, level1);
+                    #pragma unroll
+                    for (int i = 0; i < C; i++)
+                    {
+                        float dy1 = flevel * dy[i];
+                        float bd = (b11[i] + b00[i] - b10[i] - b01[i]);
+                        gu += dy1 * ((b10[i] - b00[i]) + uv1.y * bd) * sclu1;
+                        gv += dy1 * ((b01[i] - b00[i]) + uv1.x * bd) * sclu1;
+                        df += (bilerp(b00[i], b10[i], b01[i], b11[i], uv1) - bilerp(a00[i], a10[i], a01[i], a11[i], uv0)) * dy[i];
+                    }
+                }
+                g_v = cube_grad(v, gu, gv);
+                if (trilinear) { g_v.x += dfdv.x * df; g_v.y += dfdv.y * df; g_v.z += dfdv.z * df; }
+                if (trilinear && p.uv_da)
+                {
+                    g0 = cube_grad(v, dw.x * df, dw.z * df);
+                    g1 = cube_grad(v, dw.y * df, dw.w * df);
+                }
+            }
+        }
+        if (p.g_uv) { p.g_uv[pidx * 3] = g_v.x; p.g_uv[pidx * 3 + 1] = g_v.y; p.g_uv[pidx * 3 + 2] = g_v.z; }
+        if (p.g_bias) p.g_bias[pidx] = df;
+        if (p.g_uv_da)
+        {
+            float2* q = (float2*)p.g_uv_da + pidx * 3;
+            q[0] = make_float2(g0.x, g1.x); q[1] = make_float2(g0.y, g1.y); q[2] = make_float2(g0.z, g1.z);
+        }
+    }
+}
+
 // Resolve: g_out[texel][c] = pad[0][texel][c] (+ sum over levels of weight * pad[L][parent texel][c] when pulling mips),
 // written in the caller's C-channel layout.  Pull weights as in MipGradKernel (texture_kernel.cu:843-900).
 struct ResolveParams
@@ -841,17 +1180,19 @@ static int tex_fill(TexParams& p, const char* fn, const float* tex, const float*
 {
     B200DR_CHECK(filter >= 0 && filter < 4, "%s: filter_mode unsupported", fn);
     B200DR_CHECK(boundary >= 0 && boundary < 4, "%s: boundary_mode unsupported", fn);
-    B200DR_CHECK(boundary != B200DR_BOUNDARY_CUBE, "%s: cube map mode is not implemented in this build", fn);
-    B200DR_CHECK(N > 0 && H > 0 && W > 0, "%s: uv must have shape [>0, >0, >0, 2]", fn);
+    const bool cube = (boundary == B200DR_BOUNDARY_CUBE);
+    B200DR_CHECK(!cube || C <= 4, "%s: cube map mode supports at most 4 channels in this build", fn);
+    B200DR_CHECK(!cube || texW == texH, "%s: texture shape must be square in cube map mode", fn);
+    B200DR_CHECK(N > 0 && H > 0 && W > 0, "%s: uv must have shape [>0, >0, >0, %d]", fn, cube ? 3 : 2);
     B200DR_CHECK(texD > 0 && texH > 0 && texW > 0 && C > 0, "%s: tex must have shape[>0, >0, >0, >0]", fn);
     B200DR_CHECK(texD == 1 || texD == N, "%s: minibatch size mismatch between inputs tex, uv", fn);
     B200DR_CHECK(texW <= (1 << TEX_MAX_MIP) && texH <= (1 << TEX_MAX_MIP), "%s: texture size too large", fn);
     B200DR_CHECK(max_level >= 0 && max_level <= TEX_MAX_MIP, "%s: invalid mip level count", fn);
-    B200DR_CHECK((long long)texD * texH * texW < (1ll << 27), "%s: more than 2^27 texels per level are not supported", fn);
+    B200DR_CHECK((long long)texD * (cube ? 6 : 1) * texH * texW < (1ll << 27), "%s: more than 2^27 texels per level are not supported", fn);
     bool mip = (filter == B200DR_FILTER_LINEAR_MIPMAP_NEAREST || filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
     B200DR_CHECK(!mip || uv_da || bias, "%s: mipmapping filter mode requires uv_da and/or mip_level_bias input", fn);
-    B200DR_CHECK((((uintptr_t)uv) & 7) == 0, "%s: uv input tensor not aligned to float2", fn);
-    B200DR_CHECK(B200DR_ALIGNED16(uv_da), "%s: uv_da input tensor not aligned to float4", fn);
+    B200DR_CHECK(cube || (((uintptr_t)uv) & 7) == 0, "%s: uv input tensor not aligned to float2", fn);
+    B200DR_CHECK(cube ? ((((uintptr_t)uv_da) & 7) == 0) : B200DR_ALIGNED16(uv_da), "%s: uv_da input tensor not aligned to %s", fn, cube ? "float2" : "float4");
     B200DR_CHECK(B200DR_ALIGNED16(tex), "%s: padded texture level 0 not aligned to float4", fn);
     p.tex[0] = tex;
     p.mip_max = mip ? max_level : 0;
@@ -946,6 +1287,20 @@ extern "C" int b200dr_texture_fwd(const float* tex, const float* const* mip_ptrs
     TexParams p = {};
     if (tex_fill(p, "texture_fwd()", tex, mip_ptrs, max_level, uv, uv_da, mip_level_bias, N, H, W, texD, texH, texW, C, filter_mode, boundary_mode)) return 1;
     p.out = out;
+    if (boundary_mode == B200DR_BOUNDARY_CUBE)
+    {
+        size_t blocks = ((size_t)N * H * W + 255) / 256;
+        size_t bcap = (size_t)b200dr_num_sms() * 16;
+        if (blocks > bcap) blocks = bcap;
+        switch (C) {
+        case 1: texture_cube_fwd_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(p); break;
+        case 2: texture_cube_fwd_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(p); break;
+        case 3: texture_cube_fwd_kernel<3><<<(unsigned)blocks, 256, 0, stream>>>(p); break;
+        case 4: texture_cube_fwd_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(p); break;
+        }
+        B200DR_CHECK_LAUNCH("texture_fwd()");
+        return 0;
+    }
     if (C <= 4 && B200DR_ALIGNED16(out))
     {
         size_t groups = ((size_t)N * H * W + 31) / 32;
@@ -996,9 +1351,11 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
     cudaStream_t stream = (cudaStream_t)stream_;
     TexParams p = {};
     if (tex_fill(p, "texture_grad()", tex, mip_ptrs, max_level, uv, uv_da, mip_level_bias, N, H, W, texD, texH, texW, C, filter_mode, boundary_mode)) return 1;
-    B200DR_CHECK((((uintptr_t)g_uv) & 7) == 0, "texture_grad(): grad_uv output tensor not aligned to float2");
-    B200DR_CHECK(B200DR_ALIGNED16(g_uv_da), "texture_grad(): grad_uv_da output tensor not aligned to float4");
-    size_t need = b200dr_texture_grad_scratch_bytes(texD, texH, texW, C, p.mip_max);
+    const bool cube = (boundary_mode == B200DR_BOUNDARY_CUBE);
+    const int depth = cube ? 6 * texD : texD;           // cube faces are separate 2-D slices of every level
+    B200DR_CHECK(cube || (((uintptr_t)g_uv) & 7) == 0, "texture_grad(): grad_uv output tensor not aligned to float2");
+    B200DR_CHECK(cube ? ((((uintptr_t)g_uv_da) & 7) == 0) : B200DR_ALIGNED16(g_uv_da), "texture_grad(): grad_uv_da output tensor misaligned");
+    size_t need = b200dr_texture_grad_scratch_bytes(depth, texH, texW, C, p.mip_max);
     B200DR_CHECK(scratch && scratch_bytes >= need && B200DR_ALIGNED16(scratch), "texture_grad(): scratch buffer too small or misaligned");
     p.dy = dy; p.g_uv = (filter_mode != B200DR_FILTER_NEAREST) ? g_uv : 0;
     p.g_uv_da = (filter_mode == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && uv_da) ? g_uv_da : 0;
@@ -1013,12 +1370,24 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
         {
             size_t w = (texW >> L) > 1 ? (texW >> L) : 1, h = (texH >> L) > 1 ? (texH >> L) : 1;
             p.gpad[L] = (float*)s; r.gpad[L] = (const float*)s;
-            s += w * h * texD * p.Cp * sizeof(float);
+            s += w * h * depth * p.Cp * sizeof(float);
         }
     }
 
     { const char* e = getenv("B200DR_TEXDBG"); p.dbg = e ? atoi(e) : 0; }
-    if (C <= 4 && B200DR_ALIGNED16(dy))
+    if (cube)
+    {
+        size_t blocks = ((size_t)N * H * W + 255) / 256;
+        size_t bcap = (size_t)b200dr_num_sms() * 16;
+        if (blocks > bcap) blocks = bcap;
+        switch (C) {
+        case 1: texture_cube_grad_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(p); break;
+        case 2: texture_cube_grad_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(p); break;
+        case 3: texture_cube_grad_kernel<3><<<(unsigned)blocks, 256, 0, stream>>>(p); break;
+        case 4: texture_cube_grad_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(p); break;
+        }
+    }
+    else if (C <= 4 && B200DR_ALIGNED16(dy))
     {
         size_t groups = ((size_t)N * H * W + 31) / 32;
         size_t per_cta = (TEXG_THREADS / 32) * TEXG_UNROLL;
@@ -1046,7 +1415,7 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
     B200DR_CHECK_LAUNCH("texture_grad()");
 
     // resolve into the caller's layout
-    r.C = C; r.Cp = p.Cp; r.texD = texD; r.mip_max = p.mip_max; r.baseW = texW; r.baseH = texH;
+    r.C = C; r.Cp = p.Cp; r.texD = depth; r.mip_max = p.mip_max; r.baseW = texW; r.baseH = texH;
     int nlev = (pull_mips || p.mip_max == 0) ? 1 : p.mip_max + 1;
     for (int L = 0; L < nlev; L++)
     {
@@ -1055,7 +1424,7 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
         r.pull = (L == 0 && pull_mips && p.mip_max > 0) ? 1 : 0;
         r.g_out = (L == 0) ? g_tex : (g_mip_ptrs ? g_mip_ptrs[L] : 0);
         if (!r.g_out) continue;
-        size_t total = (size_t)r.texW * r.texH * texD * C;
+        size_t total = (size_t)r.texW * r.texH * depth * C;
         size_t blocks = (total + 255) / 256;
         size_t bcap = (size_t)b200dr_num_sms() * 16;
         if (blocks > bcap) blocks = bcap;

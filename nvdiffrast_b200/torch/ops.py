@@ -433,12 +433,14 @@ class TextureMipWrapper:
 
     def level(self, i):
         """Unpadded view [minibatch, height, width, channels] of mip level i >= 1 (for inspection / tests)."""
-        D, Ht, Wt, C = self.texture_size
+        D, Ht, Wt, C = self.texture_size[0], self.texture_size[-3], self.texture_size[-2], self.texture_size[-1]
         Cp = (C + 3) & ~3
-        _, offs, level_max = _mip_info("texture_construct_mip", (D, Ht, Wt, Cp), self.max_mip_level)
+        depth = 6 * D if self.cube_mode else D
+        _, offs, level_max = _mip_info("texture_construct_mip", (depth, Ht, Wt, Cp), self.max_mip_level)
         assert 1 <= i <= level_max
         w, h = max(Wt >> i, 1), max(Ht >> i, 1)
-        return self.mip[offs[i]:offs[i] + D * h * w * Cp].view(D, h, w, Cp)[..., :C]
+        lvl = self.mip[offs[i]:offs[i] + depth * h * w * Cp]
+        return (lvl.view(D, 6, h, w, Cp) if self.cube_mode else lvl.view(D, h, w, Cp))[..., :C]
 
 
 def _mip_info(fn, tex_shape, limit):
@@ -471,9 +473,12 @@ def _texture_construct_mip(tex, max_mip_level, cube_mode):
     _require(max_mip_level >= -1, fn, "invalid max_mip_level")
     dev = _check_inputs(fn, f32=[("tex", tex)])
     if cube_mode:
-        raise NotImplementedError("nvdiffrast_b200: cube map textures are not implemented yet")
-    _require(tex.dim() == 4 and min(tex.shape) > 0, fn, "tex must have shape[>0, >0, >0, >0]")
-    D, Ht, Wt, C = tex.shape
+        _require(tex.dim() == 5 and min(tex.shape) > 0 and tex.shape[1] == 6, fn, "tex must have shape[>0, 6, >0, >0, >0] in cube map mode")
+        _require(tex.shape[2] == tex.shape[3], fn, "texture shape must be square in cube map mode")
+        D, Ht, Wt, C = 6 * tex.shape[0], tex.shape[2], tex.shape[3], tex.shape[4]     # faces are separate 2-D slices
+    else:
+        _require(tex.dim() == 4 and min(tex.shape) > 0, fn, "tex must have shape[>0, >0, >0, >0]")
+        D, Ht, Wt, C = tex.shape
     Cp = (C + 3) & ~3
     total, offs, level_max = _mip_info(fn, (D, Ht, Wt, Cp), max_mip_level)
     with torch.cuda.device(dev):
@@ -497,12 +502,20 @@ def _tex_setup(fn, tex, uv, uv_da, mip_level_bias, mip_wrapper, mip_stack, filte
         _require(has_uv_da or has_bias, fn, "mipmapping filter mode requires uv_da and/or mip_level_bias input")
         _require(has_stack or (mip_wrapper is not None and mip_wrapper.mip is not None), fn, "mipmapping filter mode requires mip wrapper or mip stack input")
     dev = _check_inputs(fn, f32=[("tex", tex), ("uv", uv)])
-    if boundary_mode == 0:
-        raise NotImplementedError("nvdiffrast_b200: cube map textures are not implemented yet")
-    _require(tex.dim() == 4 and min(tex.shape) > 0, fn, "tex must have shape[>0, >0, >0, >0]")
-    _require(uv.dim() == 4 and min(uv.shape[:3]) > 0 and uv.shape[3] == 2, fn, "uv must have shape [>0, >0, >0, 2]")
-    D, Ht, Wt, C = tex.shape
+    cube = (boundary_mode == 0)
+    if cube:
+        _require(tex.dim() == 5 and min(tex.shape) > 0 and tex.shape[1] == 6, fn, "tex must have shape[>0, 6, >0, >0, >0] in cube map mode")
+        _require(uv.dim() == 4 and min(uv.shape[:3]) > 0 and uv.shape[3] == 3, fn, "uv must have shape [>0, >0, >0, 3] in cube map mode")
+        _require(tex.shape[2] == tex.shape[3], fn, "texture shape must be square in cube map mode")
+        D, Ht, Wt, C = tex.shape[0], tex.shape[2], tex.shape[3], tex.shape[4]
+        if C > 4:
+            raise NotImplementedError("nvdiffrast_b200: cube map textures support at most 4 channels in this build")
+    else:
+        _require(tex.dim() == 4 and min(tex.shape) > 0, fn, "tex must have shape[>0, >0, >0, >0]")
+        _require(uv.dim() == 4 and min(uv.shape[:3]) > 0 and uv.shape[3] == 2, fn, "uv must have shape [>0, >0, >0, 2]")
+        D, Ht, Wt, C = tex.shape
     Cp = (C + 3) & ~3
+    lvl_shape = (lambda h, w: (D, 6, h, w, C)) if cube else (lambda h, w: (D, h, w, C))
     N, H, W = uv.shape[0], uv.shape[1], uv.shape[2]
     _require(D == 1 or D == N, fn, "minibatch size mismatch between inputs tex, uv")
     _require(Wt <= (1 << _TEX_MAX_MIP_LEVEL) and Ht <= (1 << _TEX_MAX_MIP_LEVEL), fn, "texture size too large")
@@ -513,7 +526,10 @@ def _tex_setup(fn, tex, uv, uv_da, mip_level_bias, mip_wrapper, mip_stack, filte
     if enable_mip:
         if has_uv_da:
             _check_inputs(fn, f32=[("tex", tex), ("uv_da", uv_da)])
-            _require(tuple(uv_da.shape) == (N, H, W, 4), fn, "uv_da must have shape [minibatch_size, height, width, 4]")
+            if cube:
+                _require(tuple(uv_da.shape) == (N, H, W, 6), fn, "uv_da must have shape [minibatch_size, height, width, 6] in cube map mode")
+            else:
+                _require(tuple(uv_da.shape) == (N, H, W, 4), fn, "uv_da must have shape [minibatch_size, height, width, 4]")
         if has_bias:
             _check_inputs(fn, f32=[("tex", tex), ("mip_level_bias", mip_level_bias)])
             _require(tuple(mip_level_bias.shape) == (N, H, W), fn, "mip_level_bias must have shape [minibatch_size, height, width]")
@@ -530,15 +546,15 @@ def _tex_setup(fn, tex, uv, uv_da, mip_level_bias, mip_wrapper, mip_stack, filte
             for i in range(1, level_max + 1):
                 t = mip_stack[i - 1]
                 sw, sh = max(Wt >> i, 1), max(Ht >> i, 1)
-                _require(tuple(t.shape) == (D, sh, sw, C), fn, "mip level size mismatch in custom mip stack")
+                _require(tuple(t.shape) == lvl_shape(sh, sw), fn, "mip level size mismatch in custom mip stack")
                 if sw == 1 and sh == 1:
                     _require(i == level_max, fn, "mip level size mismatch in mip stack")
                 with torch.cuda.device(dev):
                     keep.append(_tex_pad(t.detach()))
                 ptrs[i] = keep[-1].data_ptr()
         else:
-            total, offs, level_max = _mip_info(fn, (D, Ht, Wt, Cp), mip_wrapper.max_mip_level)
-            _require(tuple(tex.shape) == tuple(mip_wrapper.texture_size) and not mip_wrapper.cube_mode, fn, "mip does not match texture size")
+            total, offs, level_max = _mip_info(fn, (6 * D if cube else D, Ht, Wt, Cp), mip_wrapper.max_mip_level)
+            _require(tuple(tex.shape) == tuple(mip_wrapper.texture_size) and cube == bool(mip_wrapper.cube_mode), fn, "mip does not match texture size")
             _check_inputs(fn, f32=[("tex", tex), ("mip", mip_wrapper.mip)])
             _require(mip_wrapper.mip.dim() == 1 and mip_wrapper.mip.shape[0] == total, fn, "wrapped mip tensor size mismatch")
             base = mip_wrapper.mip.data_ptr()
@@ -582,7 +598,7 @@ def _texture_grad(tex, uv, dy, uv_da, mip_level_bias, mip_wrapper, mip_stack, fi
                 g = torch.empty_like(mip_stack[i - 1])
                 g_stack.append(g)
                 g_ptrs[i] = g.data_ptr()
-        nbytes = lib.b200dr_texture_grad_scratch_bytes(D, Ht, Wt, C, level_max if enable_mip else 0)
+        nbytes = lib.b200dr_texture_grad_scratch_bytes(6 * D if boundary_mode == 0 else D, Ht, Wt, C, level_max if enable_mip else 0)
         scratch = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         _lib.call("b200dr_texture_grad", _ptr(keep[0]), ptrs, level_max, _ptr(uv), _ptr(uv_da) if (enable_mip and has_uv_da) else None,
                                            _ptr(mip_level_bias) if (enable_mip and has_bias) else None, _ptr(dy),
@@ -637,13 +653,15 @@ def texture(tex, uv, uv_da=None, mip_level_bias=None, mip=None, filter_mode='aut
     """Perform texture sampling.
 
     Args:
-        tex: float32 texture [minibatch_size, tex_height, tex_width, tex_channels] (minibatch 1 broadcasts).
-        uv: per-pixel texture coordinates [minibatch_size, height, width, 2].
-        uv_da: (optional) image-space derivatives of `uv`, [minibatch_size, height, width, 4].
+        tex: float32 texture [minibatch_size, tex_height, tex_width, tex_channels] (minibatch 1 broadcasts);
+             [minibatch_size, 6, tex_height, tex_width, tex_channels] in cube map mode.
+        uv: per-pixel texture coordinates [minibatch_size, height, width, 2]; 3-D direction vectors
+            [minibatch_size, height, width, 3] in cube map mode.
+        uv_da: (optional) image-space derivatives of `uv`, [minibatch_size, height, width, 4] (6 in cube map mode).
         mip_level_bias: (optional) per-pixel mip level bias [minibatch_size, height, width].
         mip: (optional) result of `texture_construct_mip()` or a list of tensors forming a custom mip stack.
         filter_mode: 'auto', 'nearest', 'linear', 'linear-mipmap-nearest', 'linear-mipmap-linear'.
-        boundary_mode: 'wrap', 'clamp', 'zero' ('cube' is not implemented in this build).
+        boundary_mode: 'wrap', 'clamp', 'zero', 'cube' (cube maps: up to 4 channels in this build).
         max_mip_level: limits the number of mip levels built / used.
 
     Returns:

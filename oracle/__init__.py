@@ -195,9 +195,14 @@ def mip_info(tex_shape, max_mip_level=-1):
     return int(tot), np.array(list(offs), np.int32), int(ml.value)
 
 
+def _as_slices(tex):
+    """cube maps [D,6,H,W,C] are handled as 6*D two-dimensional slices"""
+    return tex.reshape((-1,) + tex.shape[-3:]) if tex.ndim == 5 else tex
+
+
 def texture_construct_mip(tex, max_mip_level=-1):
     """-> dict(mip, offsets, max_level).  torch_texture.cpp:98-169."""
-    tex = _c32(tex)
+    tex = _as_slices(_c32(tex))
     tot, offs, ml = mip_info(tex.shape, max_mip_level)
     mip = np.zeros(max(tot, 1), np.float32)
     D, Ht, Wt, C = tex.shape
@@ -218,7 +223,7 @@ def texture_fwd(tex, uv, uv_da=None, mip_level_bias=None, mip=None, filter_mode=
     tex = _c32(tex); uv = _c32(uv); uv_da = _c32(uv_da); bias = _c32(mip_level_bias)
     m, offs, ml, _ = _mipargs(tex, filter_mode, mip, max_mip_level)
     N, H, W = uv.shape[:3]
-    D, Ht, Wt, C = tex.shape
+    D, Ht, Wt, C = tex.shape[0], tex.shape[-3], tex.shape[-2], tex.shape[-1]
     out = np.empty((N, H, W, C), np.float32)
     lib().orc_texture_fwd(_f(tex), _f(m), _i(offs), ml, _f(uv), _f(uv_da), _f(bias), N, H, W, D, Ht, Wt, C,
                           FILTER[filter_mode], BOUNDARY[boundary_mode], _f(out))
@@ -230,11 +235,11 @@ def texture_grad(tex, uv, dy, uv_da=None, mip_level_bias=None, mip=None, filter_
     tex = _c32(tex); uv = _c32(uv); dy = _c32(dy); uv_da = _c32(uv_da); bias = _c32(mip_level_bias)
     m, offs, ml, tot = _mipargs(tex, filter_mode, mip, max_mip_level)
     N, H, W = uv.shape[:3]
-    D, Ht, Wt, C = tex.shape
+    D, Ht, Wt, C = tex.shape[0], tex.shape[-3], tex.shape[-2], tex.shape[-1]
     g_tex = np.empty_like(tex)
-    g_uv = np.zeros((N, H, W, 2), np.float32) if filter_mode != 'nearest' else None
+    g_uv = np.zeros(uv.shape, np.float32) if filter_mode != 'nearest' else None
     trilinear = filter_mode == 'linear-mipmap-linear'
-    g_uv_da = np.zeros((N, H, W, 4), np.float32) if (trilinear and uv_da is not None) else None
+    g_uv_da = np.zeros(uv_da.shape, np.float32) if (trilinear and uv_da is not None) else None
     g_bias = np.zeros((N, H, W), np.float32) if (trilinear and bias is not None) else None
     lib().orc_texture_grad(_f(tex), _f(m), _i(offs), ml, ctypes.c_longlong(tot), _f(uv), _f(uv_da), _f(bias), _f(dy),
                            N, H, W, D, Ht, Wt, C, FILTER[filter_mode], BOUNDARY[boundary_mode],

@@ -1,7 +1,7 @@
 """Generate the golden vectors that pin the oracle: outputs of the UNMODIFIED reference (oracle/_ref, built by
 oracle/build_ref.sh from /root/reference) on seeded inputs, run on a B200.
 
-    gpurun -- python tests/golden/make_golden.py gpurun_out/golden      # on the GPU box
+    gpurun -- python tests/golden/make_golden.py gpurun_out/golden [cube]   # on the GPU box ("cube": only texcube_*.npz)
     cp gpurun_out/golden/*.npz tests/golden/                               # here; small fixtures, committed
 
 Only reference OUTPUTS (and the seeded inputs) are stored, no reference code.
@@ -31,10 +31,37 @@ def rnd(shape, seed):
     return np.random.default_rng(seed).normal(size=shape).astype(np.float32)
 
 
-def main(outdir):
+def texture_golden(ref, path, tex, uv, uv_da, bias, fm, bm):
+    ttex = cu(tex).requires_grad_(True); tuv = cu(uv).requires_grad_(True)
+    tda = cu(uv_da).requires_grad_(True) if uv_da is not None else None
+    tb = cu(bias).requires_grad_(True) if bias is not None else None
+    out = ref.texture(ttex, tuv, tda, tb, filter_mode=fm, boundary_mode=bm)
+    dy = rnd(out.shape, 17)
+    (out * cu(dy)).sum().backward()
+    d = dict(kind="texture", filter_mode=fm, boundary_mode=bm, tex=tex, uv=uv, dy=dy, out=npy(out), g_tex=npy(ttex.grad))
+    if uv_da is not None: d.update(uv_da=uv_da)
+    if bias is not None: d.update(bias=bias)
+    if tuv.grad is not None: d.update(g_uv=npy(tuv.grad))
+    if tda is not None and tda.grad is not None: d.update(g_uv_da=npy(tda.grad))
+    if tb is not None and tb.grad is not None: d.update(g_bias=npy(tb.grad))
+    np.savez_compressed(path, **d)
+
+
+def cube_goldens(ref, outdir):
+    """Cube-map texture cases (workloads.CUBE_CASES) -> texcube_<i>.npz"""
+    for i in range(len(wl.CUBE_CASES)):
+        c = wl.cube_texture_case(i)
+        texture_golden(ref, os.path.join(outdir, "texcube_%d.npz" % i), c["tex"], c["uv"], c["uv_da"], c["bias"], c["filter_mode"], "cube")
+
+
+def main(outdir, only=None):
     ref = load_reference()
     assert ref is not None, "oracle/_ref missing"
     os.makedirs(outdir, exist_ok=True)
+    if only == "cube":
+        cube_goldens(ref, outdir)
+        print("cube golden vectors written to", outdir)
+        return
     ctx = ref.RasterizeCudaContext()
     scenes = {
         "triangle": (wl.triangle_scene()[0], wl.triangle_scene()[1], (64, 64)),
@@ -105,8 +132,9 @@ def main(outdir):
         if use_da and tda.grad is not None: d.update(g_uv_da=npy(tda.grad))
         if use_bias and tb.grad is not None: d.update(g_bias=npy(tb.grad))
         np.savez_compressed(os.path.join(outdir, "texture_%d.npz" % i), **d)
+    cube_goldens(ref, outdir)
     print("golden vectors written to", outdir)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"))
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"), sys.argv[2] if len(sys.argv) > 2 else None)

@@ -368,6 +368,76 @@ def test_error_behaviour(dr, ctx):
 
 
 # ----------------------------------------------------------------------------------------------
+# Cube maps (boundary_mode='cube')
+
+
+def _cube_run(mod, c):
+    ttex = cu(c["tex"]).requires_grad_(True); tuv = cu(c["uv"]).requires_grad_(True)
+    tda = cu(c["uv_da"]).requires_grad_(True) if c["uv_da"] is not None else None
+    tb = cu(c["bias"]).requires_grad_(True) if c["bias"] is not None else None
+    out = mod.texture(ttex, tuv, tda, tb, filter_mode=c["filter_mode"], boundary_mode="cube")
+    dy = _rand_like(out.shape, 17)
+    (out * cu(dy)).sum().backward()
+    g = lambda t: None if (t is None or t.grad is None) else t.grad.cpu().numpy()
+    return out.detach().cpu().numpy(), dy, dict(g_tex=g(ttex), g_uv=g(tuv), g_uv_da=g(tda), g_bias=g(tb))
+
+
+@pytest.mark.parametrize("case", range(len(wl.CUBE_CASES)))
+def test_texture_cube_vs_oracle(dr, case):
+    c = wl.cube_texture_case(case)
+    out, dy, got = _cube_run(dr, c)
+    kw = dict(filter_mode=c["filter_mode"], boundary_mode="cube")
+    oo = oracle.texture_fwd(c["tex"], c["uv"], c["uv_da"], c["bias"], **kw)
+    assert_close(out, oo, 2e-5, 1e-4, "cube out", max_bad_frac=2e-3)
+    g = oracle.texture_grad(c["tex"], c["uv"], dy, c["uv_da"], c["bias"], **kw)
+    assert_grad_close(got["g_tex"], g["g_tex"], 2e-3, "g_tex")
+    if c["filter_mode"] != "nearest":
+        assert_close(got["g_uv"], g["g_uv"], 1e-3, 2e-3, "g_uv", max_bad_frac=5e-3)
+    if c["filter_mode"] == "linear-mipmap-linear":
+        if c["uv_da"] is not None:
+            assert_close(got["g_uv_da"], g["g_uv_da"], 1e-3, 2e-3, "g_uv_da", max_bad_frac=5e-3)
+        if c["bias"] is not None:
+            assert_close(got["g_bias"], g["g_bias"], 1e-4, 1e-3, "g_bias", max_bad_frac=5e-3)
+
+
+@pytest.mark.parametrize("case", range(len(wl.CUBE_CASES)))
+def test_texture_cube_vs_reference(dr, ref, case):
+    """Forward and the race-free gradients against the unmodified reference (its g_tex in the linear modes is corrupted on
+    sm_100a, see tests/golden_check.py)."""
+    c = wl.cube_texture_case(case)
+    out, _, got = _cube_run(dr, c)
+    rout, _, rgot = _cube_run(ref, c)
+    assert_close(out, rout, 2e-5, 1e-4, "cube out vs ref", max_bad_frac=2e-3)
+    if c["filter_mode"] == "nearest":
+        assert_grad_close(got["g_tex"], rgot["g_tex"], 1e-5, "g_tex")
+    for k, tol in (("g_uv", 2e-3), ("g_uv_da", 2e-3), ("g_bias", 1e-3)):
+        if rgot[k] is not None:
+            assert_close(got[k], rgot[k], 1e-3, tol, k + " vs ref", max_bad_frac=5e-3)
+
+
+def test_texture_cube_mip_wrapper_and_errors(dr):
+    rng = np.random.default_rng(31)
+    tex = rng.uniform(size=(2, 6, 16, 16, 3)).astype(np.float32)
+    mip = dr.texture_construct_mip(cu(tex), cube_mode=True)
+    om = oracle.texture_construct_mip(tex, -1)
+    off = om["offsets"]
+    for L in range(1, 5):
+        w = 16 >> L
+        assert_close(mip.level(L).cpu().numpy(), om["mip"][off[L]:off[L] + 12 * w * w * 3].reshape(2, 6, w, w, 3), 1e-6, 1e-6, "cube mip level %d" % L)
+    uv = rng.normal(size=(2, 16, 16, 3)).astype(np.float32)
+    bias = rng.uniform(0, 3, size=(2, 16, 16)).astype(np.float32)
+    a = dr.texture(cu(tex), cu(uv), mip_level_bias=cu(bias), mip=mip, boundary_mode="cube")
+    b = dr.texture(cu(tex), cu(uv), mip_level_bias=cu(bias), boundary_mode="cube")
+    assert torch.equal(a, b)
+    with pytest.raises(RuntimeError):
+        dr.texture(cu(tex), cu(uv[..., :2]), boundary_mode="cube")                       # uv must be 3-D directions
+    with pytest.raises(RuntimeError):
+        dr.texture(cu(tex[:, :, :8]), cu(uv), boundary_mode="cube", filter_mode="linear")  # faces must be square
+    with pytest.raises(RuntimeError):
+        dr.texture(cu(tex), cu(uv), mip_level_bias=cu(bias), mip=dr.texture_construct_mip(cu(tex[:, 0])), boundary_mode="cube")
+
+
+# ----------------------------------------------------------------------------------------------
 # Against the unmodified reference running on the same GPU
 
 

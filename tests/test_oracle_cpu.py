@@ -219,3 +219,72 @@ def test_oracle_matches_reference_golden(path):
     """The pin: outputs of the unmodified reference CUDA extension on a B200 (see tests/golden/make_golden.py)."""
     from golden_check import check_oracle_against_golden
     check_oracle_against_golden(np.load(path))
+
+
+# ----------------------------------------------------------------------------------------------
+# Cube maps
+
+
+def _cube_dirs(rng, n):
+    v = rng.normal(size=(1, 1, n, 3)).astype(np.float32)
+    return v / np.linalg.norm(v, axis=-1, keepdims=True)
+
+
+def test_cube_sampling_is_continuous_across_seams_and_corners():
+    """Bilinear cube sampling is a continuous function of the direction, also across face seams and around corners: a tiny
+    rotation of any direction changes the result by O(step), which fails if a seam neighbour or corner rule is wrong."""
+    rng = np.random.default_rng(40)
+    tex = rng.uniform(size=(1, 6, 4, 4, 2)).astype(np.float32)
+    v = _cube_dirs(rng, 4000)
+    # push many samples right onto seams / corners
+    v[0, 0, :1000, 0] = np.sign(v[0, 0, :1000, 0]) * np.abs(v[0, 0, :1000, 1])
+    v[0, 0, 1000:1500, 2] = np.sign(v[0, 0, 1000:1500, 2]) * np.abs(v[0, 0, 1000:1500, 1])
+    v[0, 0, 1000:1500, 0] = np.sign(v[0, 0, 1000:1500, 0]) * np.abs(v[0, 0, 1000:1500, 1])
+    v /= np.linalg.norm(v, axis=-1, keepdims=True)
+    d = rng.normal(size=v.shape).astype(np.float32) * 2e-4
+    a = oracle.texture_fwd(tex, v, filter_mode="linear", boundary_mode="cube")
+    b = oracle.texture_fwd(tex, (v + d).astype(np.float32), filter_mode="linear", boundary_mode="cube")
+    # |d(sample)/d(direction)| <= ~ w * max texel difference ~ 4; step 2e-4*sqrt(3) -> difference well below 1e-2
+    assert np.abs(a - b).max() < 1e-2
+
+
+@pytest.mark.parametrize("filter_mode", ["nearest", "linear", "linear-mipmap-linear"])
+def test_cube_texture_grad_exact_finite_difference(filter_mode):
+    """Output is linear in the texels also in cube mode (corner rule included): unit finite differences give the exact g_tex."""
+    rng = np.random.default_rng(41)
+    tex = rng.uniform(size=(1, 6, 4, 4, 2)).astype(np.float32)
+    uv = rng.normal(size=(1, 12, 12, 3)).astype(np.float32)
+    uv[0, 0, :4] = [[1, 1, 1], [-1, -1, -1], [1, -1, 1], [0, 0, 0]]
+    bias = rng.uniform(0.0, 2.0, size=(1, 12, 12)).astype(np.float32) if "mipmap" in filter_mode else None
+    dy = rng.normal(size=(1, 12, 12, 2)).astype(np.float32)
+    kw = dict(filter_mode=filter_mode, boundary_mode="cube")
+    g = oracle.texture_grad(tex, uv, dy, None, bias, **kw)["g_tex"]
+    base = oracle.texture_fwd(tex, uv, None, bias, **kw)
+    truth = np.zeros_like(tex, np.float64)
+    for idx in np.ndindex(*tex.shape):
+        t = tex.copy(); t[idx] += 1.0
+        truth[idx] = ((oracle.texture_fwd(t, uv, None, bias, **kw) - base).astype(np.float64) * dy).sum()
+    assert np.abs(g - truth).max() <= 1e-4 * np.abs(truth).max()
+
+
+def test_cube_direction_gradients_finite_difference():
+    """g_uv (3-D direction) and g_uv_da against central finite differences of the forward; pixels whose footprint or mip
+    level changes discontinuously within the step are excluded by taking the median relative error."""
+    rng = np.random.default_rng(42)
+    tex = rng.uniform(size=(1, 6, 16, 16, 1)).astype(np.float32)
+    n = 600
+    uv = (_cube_dirs(rng, n) * rng.uniform(0.5, 2.0, size=(1, 1, n, 1))).astype(np.float32)
+    uv_da = (rng.normal(size=(1, 1, n, 6)) * 0.08).astype(np.float32)
+    dy = np.ones((1, 1, n, 1), np.float32)
+    kw = dict(filter_mode="linear-mipmap-linear", boundary_mode="cube")
+    g = oracle.texture_grad(tex, uv, dy, uv_da, None, **kw)
+    f = lambda a, b: oracle.texture_fwd(tex, a, b, None, **kw)[..., 0].astype(np.float64)
+    eps = 2e-3
+    for name, arr, k in (("g_uv", uv, 3), ("g_uv_da", uv_da, 6)):
+        fd = np.zeros(arr.shape, np.float64)
+        for j in range(k):
+            p = arr.copy(); p[..., j] += eps
+            m = arr.copy(); m[..., j] -= eps
+            fd[..., j] = ((f(p, uv_da) - f(m, uv_da)) if name == "g_uv" else (f(uv, p) - f(uv, m))) / ((p[..., j] - m[..., j]).astype(np.float64))
+        err = np.abs(g[name] - fd).max(-1) / (np.abs(fd).max(-1) + 1e-3)
+        assert np.median(err) < 5e-3, (name, np.median(err))

@@ -188,3 +188,35 @@ def config_c4(n=8, res=2048, seed=0, slices=1000, stacks=501):
     pos = transform(camera_batch(n, seed, far=200.0), v)
     col = np.random.default_rng(1).uniform(size=(v.shape[0], 3)).astype(np.float32)
     return dict(pos=pos, tri=tri, attr=col, res=(res, res))
+
+
+# ----------------------------------------------------------------------------------------------
+# Cube-map texture cases (shared by tests/golden/make_golden.py and the GPU parity tests)
+
+CUBE_CASES = [  # filter_mode, use_da, use_bias, channels, texture minibatch, face size
+    ("nearest", False, False, 3, 1, 8),
+    ("linear", False, False, 1, 2, 8),
+    ("linear", False, False, 4, 1, 4),
+    ("linear-mipmap-nearest", True, False, 3, 1, 16),
+    ("linear-mipmap-linear", True, False, 4, 2, 16),
+    ("linear-mipmap-linear", True, True, 1, 1, 8),
+    ("linear-mipmap-linear", False, True, 3, 1, 16),
+]
+
+
+def cube_texture_case(i, N=2, H=40, W=56):
+    """Seeded inputs of cube-map case i: directions over the whole sphere (small faces, so seams and corners are hit all the
+    time), plus exact face-diagonal ties, axis directions, and a few invalid (zero) directions."""
+    fm, use_da, use_bias, C, D, w = CUBE_CASES[i]
+    rng = np.random.default_rng(100 + i)
+    tex = rng.uniform(size=(D, 6, w, w, C)).astype(np.float32)
+    uv = rng.normal(size=(N, H, W, 3)).astype(np.float32)
+    uv[0, 0, :8] = [[1, 1, 0.5], [1, -1, 0.2], [-1, 0.3, 1], [0.1, 1, 1], [1, 1, 1], [-1, -1, -1], [1, -1, 1], [-1, 1, -1]]
+    uv[0, 1, :6] = [[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]]
+    uv[0, 2, :3] = 0.0
+    uv[1] *= rng.uniform(0.05, 20.0, size=(H, W, 1)).astype(np.float32)
+    uv_da = (rng.normal(size=(N, H, W, 6)) * 0.05).astype(np.float32) if use_da else None
+    if use_da:
+        uv_da[1] *= np.linalg.norm(uv[1], axis=-1, keepdims=True)
+    bias = rng.uniform(-1, 3, size=(N, H, W)).astype(np.float32) if use_bias else None
+    return dict(filter_mode=fm, boundary_mode="cube", tex=tex, uv=uv, uv_da=uv_da, bias=bias)
