@@ -50,7 +50,9 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.SO_PATH
-    if _build.needs_build():
+    if os.environ.get("B200DR_LIB"):        # developer switch: A/B a tuning build made by build.build_variant()
+        path = os.environ["B200DR_LIB"]
+    elif _build.needs_build():
         try:
             _build.build()
         except Exception as e:  # no nvcc on this box: fall through to a prebuilt library if there is one

@@ -33,24 +33,33 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build_variant(name, defs):
+    """Tuning build: the same sources with extra -D flags, written to nvdiffrast_b200/variants/libb200dr_<name>.so
+    (select it with the B200DR_LIB environment variable)."""
+    out = os.path.join(_DIR, "variants", "libb200dr_%s.so" % name)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    return build(force=True, defs=list(defs), out=out, bdir=os.path.join(_DIR, "csrc", "_build", "var_" + name))
+
+
+def build(force=False, verbose=False, defs=(), out=None, bdir=None):
     if not force and not needs_build():
         return SO_PATH
-    bdir = os.path.join(_DIR, "csrc", "_build")
+    out = out or SO_PATH
+    bdir = bdir or os.path.join(_DIR, "csrc", "_build")
     os.makedirs(bdir, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(bdir, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_DIR, "csrc"),
+        cmd = [_nvcc()] + NVCC_FLAGS + list(defs) + ["-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_DIR, "csrc"),
                                         "-c", os.path.join(_DIR, "csrc", src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []
     failed = False
     for src, pr in procs:
-        out, _ = pr.communicate()
-        log.append("== %s ==\n%s" % (src, out))
+        text, _ = pr.communicate()
+        log.append("== %s ==\n%s" % (src, text))
         failed |= pr.returncode != 0
     with open(os.path.join(bdir, "build.log"), "w") as f:
         f.write("\n".join(log))
@@ -58,8 +67,8 @@ def build(force=False, verbose=False):
         sys.stderr.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed, see %s" % os.path.join(bdir, "build.log"))
-    subprocess.check_call([_nvcc(), "-shared", "-o", SO_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
-    return SO_PATH
+    subprocess.check_call([_nvcc(), "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
+    return out
 
 
 if __name__ == "__main__":

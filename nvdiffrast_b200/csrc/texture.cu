@@ -29,33 +29,50 @@ struct TexParams
     int N, H, W, texD, texH, texW, C, Cp;
     int filter, boundary, mip_max;
     int staged;
-    int dbg;                                // B200DR_TEXDBG experiment switches (0 in production)
     int chunks;                             // 256-pixel chunks over the flat N*H*W pixel array
 };
 
 static __device__ __forceinline__ int lvl_w(const TexParams& p, int l) { int v = p.texW >> l; return v > 1 ? v : 1; }
 static __device__ __forceinline__ int lvl_h(const TexParams& p, int l) { int v = p.texH >> l; return v > 1 ? v : 1; }
 
+// Filter / boundary mode and optional-input flags as seen by the device helpers.  The generic kernels fill it from the
+// launch parameters; the specialised fast kernels from template constants, so every mode switch below folds away.
+struct TexMode { int filter, boundary; bool has_da, has_bias; };
+
+static __device__ __forceinline__ TexMode tex_mode(const TexParams& p)
+{
+    TexMode m; m.filter = p.filter; m.boundary = p.boundary; m.has_da = (p.uv_da != 0); m.has_bias = (p.bias != 0);
+    return m;
+}
+template <int F, int B>
+static __device__ __forceinline__ TexMode tex_mode_static(const TexParams& p)
+{
+    TexMode m = tex_mode(p);
+    if (F >= 0) m.filter = F;
+    if (B >= 0) m.boundary = B;
+    return m;
+}
+
 // texture_kernel.cu:321-366 (2-D)
-static __device__ __forceinline__ int index_nearest(const TexParams& p, float u, float v, int tz)
+static __device__ __forceinline__ int index_nearest(const TexParams& p, const TexMode& m, float u, float v, int tz)
 {
     int w = p.texW, h = p.texH;
-    if (p.boundary == B200DR_BOUNDARY_WRAP) { u = u - (float)__float2int_rd(u); v = v - (float)__float2int_rd(v); }
+    if (m.boundary == B200DR_BOUNDARY_WRAP) { u = u - (float)__float2int_rd(u); v = v - (float)__float2int_rd(v); }
     u = u * (float)w; v = v * (float)h;
     int iu = __float2int_rd(u), iv = __float2int_rd(v);
-    if (p.boundary == B200DR_BOUNDARY_ZERO && (iu < 0 || iu >= w || iv < 0 || iv >= h)) return -1;
+    if (m.boundary == B200DR_BOUNDARY_ZERO && (iu < 0 || iu >= w || iv < 0 || iv >= h)) return -1;
     iu = min(max(iu, 0), w - 1); iv = min(max(iv, 0), h - 1);
     return iu + w * (iv + tz * h);
 }
 
 // texture_kernel.cu:368-472 (2-D): four texel indices (-1 = outside in zero mode) and the bilinear weights.
-static __device__ __forceinline__ float2 index_linear(const TexParams& p, float u, float v, int tz, int level, int4& tc)
+static __device__ __forceinline__ float2 index_linear(const TexParams& p, const TexMode& m, float u, float v, int tz, int level, int4& tc)
 {
     int w = lvl_w(p, level), h = lvl_h(p, level);
     bool clampU = false, clampV = false;
-    if (p.boundary == B200DR_BOUNDARY_WRAP) { u = u - (float)__float2int_rd(u); v = v - (float)__float2int_rd(v); }
+    if (m.boundary == B200DR_BOUNDARY_WRAP) { u = u - (float)__float2int_rd(u); v = v - (float)__float2int_rd(v); }
     u = u * (float)w - 0.5f; v = v * (float)h - 0.5f;
-    if (p.boundary == B200DR_BOUNDARY_CLAMP)
+    if (m.boundary == B200DR_BOUNDARY_CLAMP)
     {
         u = fminf(fmaxf(u, 0.f), w - 1.f); v = fminf(fmaxf(v, 0.f), h - 1.f);
         clampU = (u == 0.f || u == w - 1.f); clampV = (v == 0.f || v == h - 1.f);
@@ -63,7 +80,7 @@ static __device__ __forceinline__ float2 index_linear(const TexParams& p, float 
     int iu0 = __float2int_rd(u), iv0 = __float2int_rd(v);
     int iu1 = iu0 + (clampU ? 0 : 1), iv1 = iv0 + (clampV ? 0 : 1);
     u -= (float)iu0; v -= (float)iv0;
-    if (p.boundary == B200DR_BOUNDARY_WRAP)
+    if (m.boundary == B200DR_BOUNDARY_WRAP)
     {
         if (iu0 < 0) iu0 += w;
         if (iv0 < 0) iv0 += h;
@@ -72,7 +89,7 @@ static __device__ __forceinline__ float2 index_linear(const TexParams& p, float 
     }
     int iu0z = iu0 + tz * w * h, iu1z = iu1 + tz * w * h;
     tc.x = iu0z + w * iv0; tc.y = iu1z + w * iv0; tc.z = iu0z + w * iv1; tc.w = iu1z + w * iv1;
-    if (p.boundary == B200DR_BOUNDARY_ZERO)
+    if (m.boundary == B200DR_BOUNDARY_ZERO)
     {
         bool u0o = (iu0 < 0 || iu0 >= w), u1o = (iu1 < 0 || iu1 >= w), v0o = (iv0 < 0 || iv0 >= h), v1o = (iv1 < 0 || iv1 >= h);
         if (u0o || v0o) tc.x = -1;
@@ -85,27 +102,27 @@ static __device__ __forceinline__ float2 index_linear(const TexParams& p, float 
 
 // texture_kernel.cu:477-585 (2-D).  WANT_DW: also the derivative of the (unclamped) level w.r.t. uv_da.
 template <bool WANT_DW>
-static __device__ __forceinline__ void mip_level_from(const TexParams& p, float4 q, float bias, int& level0, int& level1, float& flevel, float4& dw);
+static __device__ __forceinline__ void mip_level_from(const TexParams& p, const TexMode& m, float4 q, float bias, int& level0, int& level1, float& flevel, float4& dw);
 
 template <bool WANT_DW>
-static __device__ __forceinline__ void mip_level(const TexParams& p, size_t pidx, int& level0, int& level1, float& flevel, float4& dw)
+static __device__ __forceinline__ void mip_level(const TexParams& p, const TexMode& m, size_t pidx, int& level0, int& level1, float& flevel, float4& dw)
 {
     level0 = 0; level1 = 0; flevel = 0.f;
-    if (p.filter == B200DR_FILTER_NEAREST || p.filter == B200DR_FILTER_LINEAR) return;
+    if (m.filter == B200DR_FILTER_NEAREST || m.filter == B200DR_FILTER_LINEAR) return;
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.uv_da) q = ld_stream_f4((const float4*)p.uv_da + pidx);
-    float bias = p.bias ? ld_stream_f(p.bias + pidx) : 0.f;
-    mip_level_from<WANT_DW>(p, q, bias, level0, level1, flevel, dw);
+    if (m.has_da) q = ld_stream_f4((const float4*)p.uv_da + pidx);
+    float bias = m.has_bias ? ld_stream_f(p.bias + pidx) : 0.f;
+    mip_level_from<WANT_DW>(p, m, q, bias, level0, level1, flevel, dw);
 }
 
 // same, with the pixel's uv_da / bias values already in registers
 template <bool WANT_DW>
-static __device__ __forceinline__ void mip_level_from(const TexParams& p, float4 q, float bias, int& level0, int& level1, float& flevel, float4& dw)
+static __device__ __forceinline__ void mip_level_from(const TexParams& p, const TexMode& m, float4 q, float bias, int& level0, int& level1, float& flevel, float4& dw)
 {
     level0 = 0; level1 = 0; flevel = 0.f;
-    if (p.filter == B200DR_FILTER_NEAREST || p.filter == B200DR_FILTER_LINEAR) return;
+    if (m.filter == B200DR_FILTER_NEAREST || m.filter == B200DR_FILTER_LINEAR) return;
     float fl = 0.f;
-    if (p.uv_da)
+    if (m.has_da)
     {
         float uscl = (float)p.texW, vscl = (float)p.texH;
         float dsdx = q.x * uscl, dsdy = q.y * uscl, dtdx = q.z * vscl, dtdy = q.w * vscl;
@@ -116,9 +133,9 @@ static __device__ __forceinline__ void mip_level_from(const TexParams& p, float4
         float l2n = 0.25f * (A - B) * (A - B) + Cc * Cc;
         float l2a = sqrtf(l2n);
         float lenMajorSqr = l2b + l2a;
-        if (WANT_DW && p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR)
+        if (WANT_DW && m.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR)
         {
-            float d = 0.72134752f / (l2n + l2a * l2b);      // 0.5 / ln 2
+            float d = __fdividef(0.72134752f, l2n + l2a * l2b);      // 0.5 / ln 2; gradient-only quantity: approximate division (2 ulp)
             float AB = d * .5f * (A - B), Cw = d * Cc, l2aw = d * l2a;
             float4 r = make_float4(uscl * (dsdx * (l2aw + AB) + dsdy * Cw), uscl * (dsdy * (l2aw - AB) + dsdx * Cw),
                                    vscl * (dtdx * (l2aw + AB) + dtdy * Cw), vscl * (dtdy * (l2aw - AB) + dtdx * Cw));
@@ -127,10 +144,10 @@ static __device__ __forceinline__ void mip_level_from(const TexParams& p, float4
         }
         fl = .5f * __log2f(lenMajorSqr);
     }
-    if (p.bias) fl += bias;
+    if (m.has_bias) fl += bias;
     fl = fminf(fmaxf(fl, 0.f), (float)p.mip_max);
     level0 = __float2int_rd(fl);
-    if (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && fl > 0.f)
+    if (m.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && fl > 0.f)
     {
         level1 = min(level0 + 1, p.mip_max);
         fl -= (float)level0;
@@ -211,6 +228,7 @@ __global__ void __launch_bounds__(256) texture_pad_kernel(const float* __restric
 
 __global__ void __launch_bounds__(TEX_THREADS) texture_fwd_kernel(const TexParams p)
 {
+    const TexMode m = tex_mode(p);
     extern __shared__ float s_out[];
     const int tid = threadIdx.x;
     const int C = p.C;
@@ -228,20 +246,20 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_fwd_kernel(const TexParam
             int tz = (p.texD == 1) ? 0 : pz;
             float2 uv = ld_stream_f2((const float2*)p.uv + pidx);
             float* o = p.staged ? (s_out + tid * C) : (p.out + pidx * C);
-            if (p.filter == B200DR_FILTER_NEAREST)
+            if (m.filter == B200DR_FILTER_NEAREST)
             {
-                int tc = index_nearest(p, uv.x, uv.y, tz);
+                int tc = index_nearest(p, m, uv.x, uv.y, tz);
                 for (int k = 0; k < p.Cp; k += 4) put4(o, k, C, texel4(p.tex[0], tc, p.Cp, k));
             }
             else
             {
                 int level0, level1; float flevel; float4 dw;
-                mip_level<false>(p, pidx, level0, level1, flevel, dw);
+                mip_level<false>(p, m, pidx, level0, level1, flevel, dw);
                 int4 tc0;
-                float2 uv0 = index_linear(p, uv.x, uv.y, tz, level0, tc0);
+                float2 uv0 = index_linear(p, m, uv.x, uv.y, tz, level0, tc0);
                 const float* t0 = p.tex[level0];
                 const int Cp = p.Cp;
-                if (p.filter != B200DR_FILTER_LINEAR_MIPMAP_LINEAR || !(flevel > 0.f))
+                if (m.filter != B200DR_FILTER_LINEAR_MIPMAP_LINEAR || !(flevel > 0.f))
                 {
                     for (int k = 0; k < Cp; k += 4)
                         put4(o, k, C, bilerp4(texel4(t0, tc0.x, Cp, k), texel4(t0, tc0.y, Cp, k), texel4(t0, tc0.z, Cp, k), texel4(t0, tc0.w, Cp, k), uv0));
@@ -249,7 +267,7 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_fwd_kernel(const TexParam
                 else
                 {
                     int4 tc1;
-                    float2 uv1 = index_linear(p, uv.x, uv.y, tz, level1, tc1);
+                    float2 uv1 = index_linear(p, m, uv.x, uv.y, tz, level1, tc1);
                     const float* t1 = p.tex[level1];
                     for (int k = 0; k < Cp; k += 4)
                     {
@@ -331,13 +349,14 @@ static __device__ __forceinline__ void accum_texel_warp(float* g, int level, int
 
 __global__ void __launch_bounds__(TEX_THREADS) texture_grad_kernel(const TexParams p)
 {
+    const TexMode m = tex_mode(p);
     extern __shared__ float s_dy[];
     __shared__ HotCache s_hot;
     const int tid = threadIdx.x;
     const int C = p.C, Cp = p.Cp;
     const size_t hw = (size_t)p.H * p.W;
     const size_t total = hw * p.N;
-    const bool trilinear = (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
+    const bool trilinear = (m.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
     HotCache* hot = (Cp <= TEX_HOT_MAXC) ? &s_hot : 0;
     if (tid < TEX_HOT_SLOTS) s_hot.key[tid] = -1;
     if (tid < TEX_HOT_SLOTS * TEX_HOT_MAXC) s_hot.val[tid / TEX_HOT_MAXC][tid % TEX_HOT_MAXC] = 0.f;
@@ -375,17 +394,17 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_grad_kernel(const TexPara
             int pz = (int)(pidx / hw);
             int tz = (p.texD == 1) ? 0 : pz;
             float2 uv = ld_stream_f2((const float2*)p.uv + pidx);
-            if (p.filter == B200DR_FILTER_NEAREST)
+            if (m.filter == B200DR_FILTER_NEAREST)
             {
-                tc0.x = index_nearest(p, uv.x, uv.y, tz);
+                tc0.x = index_nearest(p, m, uv.x, uv.y, tz);
             }
             else
             {
-                mip_level<true>(p, pidx, level0, level1, flevel, dw);
-                uv0 = index_linear(p, uv.x, uv.y, tz, level0, tc0);
+                mip_level<true>(p, m, pidx, level0, level1, flevel, dw);
+                uv0 = index_linear(p, m, uv.x, uv.y, tz, level0, tc0);
                 two = trilinear && (flevel > 0.f);
                 f0 = trilinear ? (1.f - flevel) : 1.f;
-                if (two) uv1 = index_linear(p, uv.x, uv.y, tz, level1, tc1);
+                if (two) uv1 = index_linear(p, m, uv.x, uv.y, tz, level1, tc1);
             }
         }
 
@@ -394,7 +413,7 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_grad_kernel(const TexPara
         {
             // few distinct texels in this warp's 32 pixels -> pre-reduce runs; otherwise scatter directly
             const bool reduce = __popc(warp_runs(act ? (tc0.x ^ (level0 << 27)) : -1).heads) <= 10;
-            if (p.filter == B200DR_FILTER_NEAREST)
+            if (m.filter == B200DR_FILTER_NEAREST)
             {
                 accum_texel_warp(p.gpad[0], 0, tc0.x, C, Cp, 1.f, pDy, reduce, hot, 0);
             }
@@ -422,7 +441,7 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_grad_kernel(const TexPara
         if (inb)
         {
             float gu = 0.f, gv = 0.f, df = 0.f;
-            if (act && p.filter != B200DR_FILTER_NEAREST)
+            if (act && m.filter != B200DR_FILTER_NEAREST)
             {
                 const float* t0 = p.tex[level0];
                 const float* t1 = p.tex[level1];
@@ -492,23 +511,76 @@ static __device__ __forceinline__ void unpack4(float4 v, float (&o)[C])
     if (C > 3) o[3 % C] = v.w;
 }
 
-#define TEXF_UNROLL 2
+// Result cache for "uniform" pixel groups.  Rendered images contain large regions whose 32-pixel groups carry bitwise
+// identical texture coordinates (the background: uv = uv_da = 0).  Every such group has the same mip level, texel quad,
+// weights and fetched texels, so a warp remembers the inputs of the last such group it fully evaluated (key: uv, uv_da,
+// bias bits and the texture slice) together with the results that depend only on them, and later groups that match the key
+// lane for lane skip level selection, indexing and texel fetches.  The slot lives in shared memory (one per warp); `valid`
+// is a warp-uniform register.  Same arithmetic, same results; non-matching groups pay ~12 instructions for the probe.
+struct UniKey { unsigned k[8]; };
+#ifdef TEX_COUNT_HITS
+__device__ unsigned long long g_tex_counters[8];      // [0] fwd hit [1] fwd miss [2] fwd fill [3] grad hit [4] grad miss [5] grad fill [6] grad uniform
+#define TEX_COUNT(i) do { if (lane == 0) atomicAdd(&g_tex_counters[i], 1ull); } while (0)
+#else
+#define TEX_COUNT(i) do { } while (0)
+#endif
 
-template <int C>
-__global__ void __launch_bounds__(TEX_THREADS) texture_fwd_fast(const TexParams p)
+static __device__ __forceinline__ bool uni_match(const UniKey* slot, float2 uv, float4 da, float bias, int tz)
 {
+    uint4 a = *(const uint4*)&slot->k[0], b = *(const uint4*)&slot->k[4];
+    unsigned diff = (__float_as_uint(uv.x) ^ a.x) | (__float_as_uint(uv.y) ^ a.y) | (__float_as_uint(da.x) ^ a.z) | (__float_as_uint(da.y) ^ a.w)
+                  | (__float_as_uint(da.z) ^ b.x) | (__float_as_uint(da.w) ^ b.y) | (__float_as_uint(bias) ^ b.z) | ((unsigned)tz ^ b.w);
+    return diff == 0u;
+}
+
+// all 32 lanes carry the same inputs as lane 0?  (cheap one-value prefilter first: almost every non-uniform group stops there)
+static __device__ __forceinline__ bool uni_identical(float2 uv, float4 da, float bias, int tz)
+{
+    const unsigned full = 0xffffffffu;
+    unsigned x0 = __shfl_sync(full, __float_as_uint(uv.x), 0);
+    if (!__all_sync(full, x0 == __float_as_uint(uv.x))) return false;
+    unsigned d = (__shfl_sync(full, __float_as_uint(uv.y), 0) ^ __float_as_uint(uv.y));
+    d |= (__shfl_sync(full, __float_as_uint(da.x), 0) ^ __float_as_uint(da.x));
+    d |= (__shfl_sync(full, __float_as_uint(da.y), 0) ^ __float_as_uint(da.y));
+    d |= (__shfl_sync(full, __float_as_uint(da.z), 0) ^ __float_as_uint(da.z));
+    d |= (__shfl_sync(full, __float_as_uint(da.w), 0) ^ __float_as_uint(da.w));
+    d |= (__shfl_sync(full, __float_as_uint(bias), 0) ^ __float_as_uint(bias));
+    d |= ((unsigned)__shfl_sync(full, tz, 0) ^ (unsigned)tz);
+    return __all_sync(full, d == 0u);
+}
+
+static __device__ __forceinline__ void uni_store_key(UniKey* slot, float2 uv, float4 da, float bias, int tz)
+{
+    *(uint4*)&slot->k[0] = make_uint4(__float_as_uint(uv.x), __float_as_uint(uv.y), __float_as_uint(da.x), __float_as_uint(da.y));
+    *(uint4*)&slot->k[4] = make_uint4(__float_as_uint(da.z), __float_as_uint(da.w), __float_as_uint(bias), (unsigned)tz);
+}
+
+#ifndef TEXF_UNROLL
+#define TEXF_UNROLL 2
+#endif
+#ifndef TEXF_MINB
+#define TEXF_MINB 4
+#endif
+
+template <int C, int F, int B>
+__global__ void __launch_bounds__(TEX_THREADS, TEXF_MINB) texture_fwd_fast(const TexParams p)
+{
+    const TexMode m = tex_mode_static<F, B>(p);
     constexpr int SK = (C == 3) ? 3 : 1;
     __shared__ __align__(16) float s_stage[TEX_THREADS / 32][32 * SK];
+    __shared__ __align__(16) UniKey s_key[TEX_THREADS / 32];
+    __shared__ __align__(16) float4 s_val[TEX_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t hw = (size_t)p.H * p.W;
     const size_t total = hw * p.N;
     const size_t groups = (total + 31) >> 5;
     const size_t wstride = (size_t)gridDim.x * (TEX_THREADS / 32);
-    const bool mip = (p.filter == B200DR_FILTER_LINEAR_MIPMAP_NEAREST || p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
+    const bool mip = (m.filter == B200DR_FILTER_LINEAR_MIPMAP_NEAREST || m.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
+    bool cached = false;                                // warp-uniform: s_key/s_val[warp] hold a uniform group's inputs/result
 
     for (size_t g0 = (size_t)blockIdx.x * (TEX_THREADS / 32) + warp; g0 < groups; g0 += TEXF_UNROLL * wstride)
     {
-        // issue the streaming loads of both groups first
+        // issue the streaming loads of all groups in flight first
         float2 uv[TEXF_UNROLL]; float4 da[TEXF_UNROLL]; float bias[TEXF_UNROLL]; bool inb[TEXF_UNROLL];
         #pragma unroll
         for (int u = 0; u < TEXF_UNROLL; u++)
@@ -519,8 +591,8 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_fwd_fast(const TexParams 
             if (inb[u])
             {
                 uv[u] = ld_stream_f2((const float2*)p.uv + pidx);
-                if (mip && p.uv_da) da[u] = ld_stream_f4((const float4*)p.uv_da + pidx);
-                if (mip && p.bias) bias[u] = ld_stream_f(p.bias + pidx);
+                if (mip && m.has_da) da[u] = ld_stream_f4((const float4*)p.uv_da + pidx);
+                if (mip && m.has_bias) bias[u] = ld_stream_f(p.bias + pidx);
             }
         }
         #pragma unroll
@@ -529,37 +601,48 @@ __global__ void __launch_bounds__(TEX_THREADS) texture_fwd_fast(const TexParams 
             size_t g = g0 + u * wstride;
             if (g >= groups) continue;                  // warp-uniform
             size_t pidx = g * 32 + lane;
+            const bool full = (g * 32 + 32 <= total);
+            const int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
             float o[C];
-            #pragma unroll
-            for (int i = 0; i < C; i++) o[i] = 0.f;
+            if (cached && full && __all_sync(0xffffffffu, uni_match(&s_key[warp], uv[u], da[u], bias[u], tz)))
+            {
+                TEX_COUNT(0);
+                unpack4<C>(s_val[warp], o);
+                warp_store_aos<C>(p.out + g * 32 * C, o, lane, true, true, s_stage[warp]);
+                continue;
+            }
+            TEX_COUNT(1);
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
             if (inb[u])
             {
-                int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
-                if (p.filter == B200DR_FILTER_NEAREST)
-                {
-                    unpack4<C>(texel4(p.tex[0], index_nearest(p, uv[u].x, uv[u].y, tz), 4, 0), o);
-                }
+                if (m.filter == B200DR_FILTER_NEAREST) r = texel4(p.tex[0], index_nearest(p, m, uv[u].x, uv[u].y, tz), 4, 0);
                 else
                 {
                     int level0, level1; float flevel; float4 dw;
-                    mip_level_from<false>(p, da[u], bias[u], level0, level1, flevel, dw);
+                    mip_level_from<false>(p, m, da[u], bias[u], level0, level1, flevel, dw);
                     int4 tc0;
-                    float2 uv0 = index_linear(p, uv[u].x, uv[u].y, tz, level0, tc0);
+                    float2 uv0 = index_linear(p, m, uv[u].x, uv[u].y, tz, level0, tc0);
                     const float* t0 = p.tex[level0];
-                    float4 a = bilerp4(texel4(t0, tc0.x, 4, 0), texel4(t0, tc0.y, 4, 0), texel4(t0, tc0.z, 4, 0), texel4(t0, tc0.w, 4, 0), uv0);
-                    if (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && flevel > 0.f)
+                    r = bilerp4(texel4(t0, tc0.x, 4, 0), texel4(t0, tc0.y, 4, 0), texel4(t0, tc0.z, 4, 0), texel4(t0, tc0.w, 4, 0), uv0);
+                    if (m.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && flevel > 0.f)
                     {
                         int4 tc1;
-                        float2 uv1 = index_linear(p, uv[u].x, uv[u].y, tz, level1, tc1);
+                        float2 uv1 = index_linear(p, m, uv[u].x, uv[u].y, tz, level1, tc1);
                         const float* t1 = p.tex[level1];
                         float4 b = bilerp4(texel4(t1, tc1.x, 4, 0), texel4(t1, tc1.y, 4, 0), texel4(t1, tc1.z, 4, 0), texel4(t1, tc1.w, 4, 0), uv1);
-                        a = make_float4(lerpf(a.x, b.x, flevel), lerpf(a.y, b.y, flevel), lerpf(a.z, b.z, flevel), lerpf(a.w, b.w, flevel));
+                        r = make_float4(lerpf(r.x, b.x, flevel), lerpf(r.y, b.y, flevel), lerpf(r.z, b.z, flevel), lerpf(r.w, b.w, flevel));
                     }
-                    unpack4<C>(a, o);
                 }
             }
-            bool full = (g * 32 + 32 <= total);
+            unpack4<C>(r, o);
             warp_store_aos<C>(p.out + g * 32 * C, o, lane, inb[u], full, s_stage[warp]);
+            if (full && uni_identical(uv[u], da[u], bias[u], tz))
+            {
+                TEX_COUNT(2);
+                if (lane == 0) { uni_store_key(&s_key[warp], uv[u], da[u], bias[u], tz); s_val[warp] = r; }
+                __syncwarp();
+                cached = true;
+            }
         }
     }
 }
@@ -588,31 +671,38 @@ template <int C>
 struct Pending
 {
     int key; int u, v;          // identity: texel quad (tc0.x ^ level << 27) and the bit patterns of the bilinear weights
-    int level; int4 tc; float4 w;
+    int level; int4 tc; float4 w;   // level < 0: empty
     float sum[C];
 };
 
 template <int C>
 static __device__ __forceinline__ void pending_flush(Pending<C>& pd, const TexParams& p, int lane)
 {
-    if (pd.key != -1 && lane < 4)
+    if (pd.level >= 0 && lane < 4)
     {
         int tc = (lane == 0) ? pd.tc.x : (lane == 1) ? pd.tc.y : (lane == 2) ? pd.tc.z : pd.tc.w;
         float w = (lane == 0) ? pd.w.x : (lane == 1) ? pd.w.y : (lane == 2) ? pd.w.z : pd.w.w;
         scatter_tap<C>(p.gpad[pd.level], tc, w, pd.sum);
     }
-    pd.key = -1;
+    pd.level = -1;                                      // empty
 }
 
+#ifndef TEXG_THREADS
 #define TEXG_THREADS 128
-#define TEXG_UNROLL  2
+#endif
+#ifndef TEXG_UNROLL
+#define TEXG_UNROLL  1
+#endif
+#ifndef TEXG_MINB
+#define TEXG_MINB 5
+#endif
 
 // Streaming inputs of one 32-pixel group, loaded up front (two groups are in flight per warp).
 template <int C>
 struct TexGradIn { AosRaw<C> dy; float2 uv; float4 da; float bias; bool inb, full; size_t g; };
 
 template <int C>
-static __device__ __forceinline__ void texgrad_issue(const TexParams& p, size_t g, size_t groups, size_t total, int lane, TexGradIn<C>& in)
+static __device__ __forceinline__ void texgrad_issue(const TexParams& p, const TexMode& m, size_t g, size_t groups, size_t total, int lane, TexGradIn<C>& in)
 {
     in.g = g;
     size_t pidx = g * 32 + lane;
@@ -622,25 +712,54 @@ static __device__ __forceinline__ void texgrad_issue(const TexParams& p, size_t 
     if (in.inb)
     {
         in.uv = ld_stream_f2((const float2*)p.uv + pidx);
-        if (p.uv_da) in.da = ld_stream_f4((const float4*)p.uv_da + pidx);
-        if (p.bias) in.bias = ld_stream_f(p.bias + pidx);
+        if (m.has_da) in.da = ld_stream_f4((const float4*)p.uv_da + pidx);
+        if (m.has_bias) in.bias = ld_stream_f(p.bias + pidx);
     }
     warp_load_aos_issue<C>(p.dy + g * 32 * C, in.dy, lane, in.inb, in.full);
 }
 
+// Per-warp slot of the uniform-group cache in the backward pass: key + d(out)/d(u,v) per channel (gu = sum_i dy_i * ku_i).
+struct UniGradSlot { UniKey key; float4 ku, kv; };
+
 template <int C>
-static __device__ __forceinline__ void texgrad_group(const TexParams& p, const TexGradIn<C>& in, Pending<C>& pd, int lane, float* sw,
-                                                     size_t hw, bool trilinear)
+static __device__ __forceinline__ float dot4(float4 k, const float (&dy)[C])
+{
+    float r = dy[0] * k.x;
+    if (C > 1) r += dy[1 % C] * k.y;
+    if (C > 2) r += dy[2 % C] * k.z;
+    if (C > 3) r += dy[3 % C] * k.w;
+    return r;
+}
+
+template <int C, int B>
+static __device__ __forceinline__ void texgrad_group(const TexParams& p, const TexMode& m, const TexGradIn<C>& in, Pending<C>& pd, bool& cached,
+                                                     UniGradSlot* slot, int lane, float* sw, size_t hw, bool trilinear)
 {
     const size_t pidx = in.g * 32 + lane;
     const bool inb = in.inb;
     float dy[C];
     warp_load_aos_finish<C>(p.dy + in.g * 32 * C, in.dy, dy, lane, inb, in.full, sw);
+    const float2 uv = in.uv;
+    const int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
+
+    // Uniform group seen before (see UniKey): level, quad, weights and texels are those of the cached group, which was a
+    // single-level (flevel == 0) group, so g_bias = g_uv_da = 0; the texel gradient joins the pending sums of that quad.
+    if (cached && in.full && __all_sync(0xffffffffu, uni_match(&slot->key, uv, in.da, in.bias, tz)))
+    {
+        TEX_COUNT(3);
+        #pragma unroll
+        for (int i = 0; i < C; i++) pd.sum[i] += warp_sum(dy[i]);
+        if (p.g_uv) st_stream_f2((float2*)p.g_uv + pidx, make_float2(dot4<C>(slot->ku, dy), dot4<C>(slot->kv, dy)));
+        if (p.g_bias) st_stream_f(p.g_bias + pidx, 0.f);
+        if (p.g_uv_da) st_stream_f4((float4*)p.g_uv_da + pidx, make_float4(0.f, 0.f, 0.f, 0.f));
+        return;
+    }
+
+    TEX_COUNT(4);
     unsigned dmax = 0u;
     #pragma unroll
     for (int i = 0; i < C; i++) dmax |= __float_as_uint(dy[i]);
     bool act = inb && (__uint_as_float(dmax) != 0.f);
-    const float2 uv = in.uv;
 
     float gu = 0.f, gv = 0.f, df = 0.f;
     float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -653,19 +772,18 @@ static __device__ __forceinline__ void texgrad_group(const TexParams& p, const T
         float f0 = 1.f;
         if (act)
         {
-            int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
-            if (p.filter == B200DR_FILTER_NEAREST) tc0.x = index_nearest(p, uv.x, uv.y, tz);
+            if (m.filter == B200DR_FILTER_NEAREST) tc0.x = index_nearest(p, m, uv.x, uv.y, tz);
             else
             {
-                mip_level_from<true>(p, in.da, in.bias, level0, level1, flevel, dw);
-                uv0 = index_linear(p, uv.x, uv.y, tz, level0, tc0);
+                mip_level_from<true>(p, m, in.da, in.bias, level0, level1, flevel, dw);
+                uv0 = index_linear(p, m, uv.x, uv.y, tz, level0, tc0);
                 two = trilinear && (flevel > 0.f);
                 f0 = trilinear ? (1.f - flevel) : 1.f;
-                if (two) uv1 = index_linear(p, uv.x, uv.y, tz, level1, tc1);
+                if (two) uv1 = index_linear(p, m, uv.x, uv.y, tz, level1, tc1);
             }
         }
         float uv011 = uv0.x * uv0.y, uv010 = uv0.x - uv011, uv001 = uv0.y - uv011, uv000 = 1.f - uv0.x - uv001;
-        float4 w0 = (p.filter == B200DR_FILTER_NEAREST) ? make_float4(1.f, 0.f, 0.f, 0.f)
+        float4 w0 = (m.filter == B200DR_FILTER_NEAREST) ? make_float4(1.f, 0.f, 0.f, 0.f)
                                                         : make_float4(uv000 * f0, uv010 * f0, uv001 * f0, uv011 * f0);
 
         // Whole warp on one texel quad with identical weights?  (shuffles first: no short-circuit around collectives)
@@ -674,31 +792,33 @@ static __device__ __forceinline__ void texgrad_group(const TexParams& p, const T
         int u0 = __shfl_sync(0xffffffffu, __float_as_int(w0.y), 0);
         int v0 = __shfl_sync(0xffffffffu, __float_as_int(w0.z), 0);
         bool same = act && !two && (key0 == k0) && (__float_as_int(w0.y) == u0) && (__float_as_int(w0.z) == v0);
-        bool uniform = __all_sync(0xffffffffu, same);
+        const bool uniform = __all_sync(0xffffffffu, same);
+        bool fill = false;
         if (uniform)
         {
-            if (!(p.dbg & 2))
+            TEX_COUNT(6);
+            if (pd.level < 0 || pd.key != key0 || pd.u != u0 || pd.v != v0)
             {
-                if (pd.key != key0 || pd.u != u0 || pd.v != v0)
-                {
-                    pending_flush<C>(pd, p, lane);
-                    pd.key = key0; pd.u = u0; pd.v = v0; pd.level = level0; pd.tc = tc0; pd.w = w0;
-                    #pragma unroll
-                    for (int i = 0; i < C; i++) pd.sum[i] = 0.f;
-                }
+                pending_flush<C>(pd, p, lane);
+                pd.key = key0; pd.u = u0; pd.v = v0; pd.level = level0; pd.tc = tc0; pd.w = w0;
                 #pragma unroll
-                for (int i = 0; i < C; i++) pd.sum[i] += warp_sum(dy[i]);
+                for (int i = 0; i < C; i++) pd.sum[i] = 0.f;
+                cached = false;                         // the cache is only valid while its quad is the pending one
             }
+            #pragma unroll
+            for (int i = 0; i < C; i++) pd.sum[i] += warp_sum(dy[i]);
+            fill = !cached && in.full && (m.filter != B200DR_FILTER_NEAREST) && uni_identical(uv, in.da, in.bias, tz);
         }
-        else if (!(p.dbg & 1))
+        else
         {
             // Neighbouring pixels of a magnified texture sit on the same texel quad: sum runs of up to 4 equal quads
             // with two shuffle steps, so a quad receives one vector reduction per run instead of one per pixel
             // (same-address reductions inside one instruction serialise).  Skipped when the warp has few duplicates.
-            WarpRuns runs = warp_runs_max4((act && !two && tc0.x >= 0 && tc0.w >= 0) ? key0 : -1 - lane, tc0.w);    // first and diagonal tap pin the whole quad
-            const bool merge = !(p.dbg & 8) && (__popc(runs.heads) <= 24);
+            const bool pinned = (B == B200DR_BOUNDARY_WRAP || B == B200DR_BOUNDARY_CLAMP) ? true : (tc0.x >= 0 && tc0.w >= 0);
+            WarpRuns runs = warp_runs_max4((act && !two && pinned) ? key0 : -1 - lane, tc0.w);    // first and diagonal tap pin the whole quad
+            const bool merge = (__popc(runs.heads) <= 24);
             float* g0 = p.gpad[level0];
-            const int ntap = (p.filter == B200DR_FILTER_NEAREST) ? 1 : 4;
+            const int ntap = (m.filter == B200DR_FILTER_NEAREST) ? 1 : 4;
             for (int t = 0; t < ntap; t++)
             {
                 int tc = (t == 0) ? tc0.x : (t == 1) ? tc0.y : (t == 2) ? tc0.z : tc0.w;
@@ -725,20 +845,33 @@ static __device__ __forceinline__ void texgrad_group(const TexParams& p, const T
             }
         }
 
-        if (act && p.filter != B200DR_FILTER_NEAREST && !(p.dbg & 4))
+        if (act && m.filter != B200DR_FILTER_NEAREST)
         {
             const float* t0 = p.tex[level0];
             float sclu0 = (float)lvl_w(p, level0), sclv0 = (float)lvl_h(p, level0);
             float a00[C], a10[C], a01[C], a11[C];
             unpack4<C>(texel4(t0, tc0.x, 4, 0), a00); unpack4<C>(texel4(t0, tc0.y, 4, 0), a10);
             unpack4<C>(texel4(t0, tc0.z, 4, 0), a01); unpack4<C>(texel4(t0, tc0.w, 4, 0), a11);
+            float ku[4] = { 0.f, 0.f, 0.f, 0.f }, kv[4] = { 0.f, 0.f, 0.f, 0.f };
             #pragma unroll
             for (int i = 0; i < C; i++)
             {
-                float dy0 = f0 * dy[i];
                 float ad = (a11[i] + a00[i] - a10[i] - a01[i]);
-                gu += dy0 * ((a10[i] - a00[i]) + uv0.y * ad) * sclu0;
-                gv += dy0 * ((a01[i] - a00[i]) + uv0.x * ad) * sclv0;
+                ku[i] = f0 * ((a10[i] - a00[i]) + uv0.y * ad) * sclu0;
+                kv[i] = f0 * ((a01[i] - a00[i]) + uv0.x * ad) * sclv0;
+                gu += dy[i] * ku[i];
+                gv += dy[i] * kv[i];
+            }
+            if (fill)                                   // warp-uniform; every lane holds the same ku / kv
+            {
+                TEX_COUNT(5);
+                if (lane == 0)
+                {
+                    uni_store_key(&slot->key, uv, in.da, in.bias, tz);
+                    slot->ku = make_float4(ku[0], ku[1], ku[2], ku[3]); slot->kv = make_float4(kv[0], kv[1], kv[2], kv[3]);
+                }
+                __syncwarp();
+                cached = true;
             }
             if (two)
             {
@@ -769,30 +902,33 @@ static __device__ __forceinline__ void texgrad_group(const TexParams& p, const T
     }
 }
 
-template <int C>
-__global__ void __launch_bounds__(TEXG_THREADS, 5) texture_grad_fast(const TexParams p)
+template <int C, int F, int B>
+__global__ void __launch_bounds__(TEXG_THREADS, TEXG_MINB) texture_grad_fast(const TexParams p)
 {
+    const TexMode m = tex_mode_static<F, B>(p);
     constexpr int SK = (C == 3) ? 3 : 1;
     __shared__ __align__(16) float s_stage[TEXG_THREADS / 32][32 * SK];
+    __shared__ __align__(16) UniGradSlot s_slot[TEXG_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t hw = (size_t)p.H * p.W;
     const size_t total = hw * p.N;
     const size_t groups = (total + 31) >> 5;
     const size_t wstride = (size_t)gridDim.x * (TEXG_THREADS / 32);
-    const bool trilinear = (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
+    const bool trilinear = (m.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
     Pending<C> pd;
-    pd.key = -1; pd.u = 0; pd.v = 0; pd.level = 0; pd.tc = make_int4(-1, -1, -1, -1); pd.w = make_float4(0.f, 0.f, 0.f, 0.f);
+    pd.key = -1; pd.u = 0; pd.v = 0; pd.level = -1; pd.tc = make_int4(-1, -1, -1, -1); pd.w = make_float4(0.f, 0.f, 0.f, 0.f);
     #pragma unroll
     for (int i = 0; i < C; i++) pd.sum[i] = 0.f;
+    bool cached = false;
 
     for (size_t g0 = (size_t)blockIdx.x * (TEXG_THREADS / 32) + warp; g0 < groups; g0 += TEXG_UNROLL * wstride)
     {
         TexGradIn<C> in[TEXG_UNROLL];
         #pragma unroll
-        for (int u = 0; u < TEXG_UNROLL; u++) texgrad_issue<C>(p, g0 + u * wstride, groups, total, lane, in[u]);
+        for (int u = 0; u < TEXG_UNROLL; u++) texgrad_issue<C>(p, m, g0 + u * wstride, groups, total, lane, in[u]);
         #pragma unroll
         for (int u = 0; u < TEXG_UNROLL; u++)
-            if (in[u].g < groups) texgrad_group<C>(p, in[u], pd, lane, s_stage[warp], hw, trilinear);      // warp-uniform
+            if (in[u].g < groups) texgrad_group<C, B>(p, m, in[u], pd, cached, &s_slot[warp], lane, s_stage[warp], hw, trilinear);      // warp-uniform
     }
     pending_flush<C>(pd, p, lane);
 }
@@ -1005,6 +1141,7 @@ static __device__ __forceinline__ void cube_load_dirs(const TexParams& p, size_t
 template <int C>
 __global__ void __launch_bounds__(256) texture_cube_fwd_kernel(const TexParams p)
 {
+    const TexMode m = tex_mode(p);
     const size_t hw = (size_t)p.H * p.W, total = hw * p.N;
     for (size_t pidx = (size_t)blockIdx.x * 256 + threadIdx.x; pidx < total; pidx += (size_t)gridDim.x * 256)
     {
@@ -1012,18 +1149,18 @@ __global__ void __launch_bounds__(256) texture_cube_fwd_kernel(const TexParams p
         float3 v, dX, dY;
         cube_load_dirs(p, pidx, v, dX, dY);
         float o[C];
-        if (p.filter == B200DR_FILTER_NEAREST) unpack4<C>(texel4(p.tex[0], cube_nearest(p, v, tz), 4, 0), o);
+        if (m.filter == B200DR_FILTER_NEAREST) unpack4<C>(texel4(p.tex[0], cube_nearest(p, v, tz), 4, 0), o);
         else
         {
             int level0, level1; float flevel; float4 dw;
             float bias = p.bias ? ld_stream_f(p.bias + pidx) : 0.f;
-            mip_level_from<false>(p, cube_grad_st(v, dX, dY), bias, level0, level1, flevel, dw);
+            mip_level_from<false>(p, m, cube_grad_st(v, dX, dY), bias, level0, level1, flevel, dw);
             int4 tc0; bool cor0;
             float2 uv0 = cube_index_linear(p, v, tz, level0, tc0, cor0);
             float4 a, b, c, d;
             cube_fetch(p.tex[level0], tc0, cor0, a, b, c, d);
             float4 r = bilerp4(a, b, c, d, uv0);
-            if (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && flevel > 0.f)
+            if (m.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && flevel > 0.f)
             {
                 int4 tc1; bool cor1;
                 float2 uv1 = cube_index_linear(p, v, tz, level1, tc1, cor1);
@@ -1041,8 +1178,9 @@ __global__ void __launch_bounds__(256) texture_cube_fwd_kernel(const TexParams p
 template <int C>
 __global__ void __launch_bounds__(256) texture_cube_grad_kernel(const TexParams p)
 {
+    const TexMode m = tex_mode(p);
     const size_t hw = (size_t)p.H * p.W, total = hw * p.N;
-    const bool trilinear = (p.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
+    const bool trilinear = (m.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
     for (size_t pidx = (size_t)blockIdx.x * 256 + threadIdx.x; pidx < total; pidx += (size_t)gridDim.x * 256)
     {
         float dy[C];
@@ -1056,12 +1194,12 @@ __global__ void __launch_bounds__(256) texture_cube_grad_kernel(const TexParams 
             int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
             float3 v, dX, dY;
             cube_load_dirs(p, pidx, v, dX, dY);
-            if (p.filter == B200DR_FILTER_NEAREST) scatter_tap<C>(p.gpad[0], cube_nearest(p, v, tz), 1.f, dy);
+            if (m.filter == B200DR_FILTER_NEAREST) scatter_tap<C>(p.gpad[0], cube_nearest(p, v, tz), 1.f, dy);
             else
             {
                 int level0, level1; float flevel; float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
                 float bias = p.bias ? ld_stream_f(p.bias + pidx) : 0.f;
-                mip_level_from<true>(p, cube_grad_st(v, dX, dY), bias, level0, level1, flevel, dw);
+                mip_level_from<true>(p, m, cube_grad_st(v, dX, dY), bias, level0, level1, flevel, dw);
                 float3 dfdv = make_float3(0.f, 0.f, 0.f);
                 if (trilinear && p.uv_da)
                 {
@@ -1231,6 +1369,40 @@ static long long mip_info(int texW, int texH, int texD, int C, int limit, int* o
     return total;
 }
 
+// Fast-kernel dispatch: the common mode pairs (bilinear / trilinear x wrap / clamp) get kernels with the mode switches
+// folded at compile time; every other combination runs the same code with run-time (warp-uniform) switches.
+template <int F, int B>
+static void launch_fast_fwd_c(const TexParams& p, unsigned blocks, cudaStream_t stream)
+{
+    switch (p.C) {
+    case 1: texture_fwd_fast<1, F, B><<<blocks, TEX_THREADS, 0, stream>>>(p); break;
+    case 2: texture_fwd_fast<2, F, B><<<blocks, TEX_THREADS, 0, stream>>>(p); break;
+    case 3: texture_fwd_fast<3, F, B><<<blocks, TEX_THREADS, 0, stream>>>(p); break;
+    case 4: texture_fwd_fast<4, F, B><<<blocks, TEX_THREADS, 0, stream>>>(p); break;
+    }
+}
+template <int F, int B>
+static void launch_fast_grad_c(const TexParams& p, unsigned blocks, cudaStream_t stream)
+{
+    switch (p.C) {
+    case 1: texture_grad_fast<1, F, B><<<blocks, TEXG_THREADS, 0, stream>>>(p); break;
+    case 2: texture_grad_fast<2, F, B><<<blocks, TEXG_THREADS, 0, stream>>>(p); break;
+    case 3: texture_grad_fast<3, F, B><<<blocks, TEXG_THREADS, 0, stream>>>(p); break;
+    case 4: texture_grad_fast<4, F, B><<<blocks, TEXG_THREADS, 0, stream>>>(p); break;
+    }
+}
+#define TEX_MODE_DISPATCH(FN)                                                                                                    \
+    do {                                                                                                                         \
+        const int f = p.filter, b = p.boundary;                                                                                  \
+        if      (f == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && b == B200DR_BOUNDARY_WRAP)  FN<B200DR_FILTER_LINEAR_MIPMAP_LINEAR, B200DR_BOUNDARY_WRAP>(p, blocks, stream);  \
+        else if (f == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && b == B200DR_BOUNDARY_CLAMP) FN<B200DR_FILTER_LINEAR_MIPMAP_LINEAR, B200DR_BOUNDARY_CLAMP>(p, blocks, stream); \
+        else if (f == B200DR_FILTER_LINEAR && b == B200DR_BOUNDARY_WRAP)                FN<B200DR_FILTER_LINEAR, B200DR_BOUNDARY_WRAP>(p, blocks, stream);                \
+        else if (f == B200DR_FILTER_LINEAR && b == B200DR_BOUNDARY_CLAMP)               FN<B200DR_FILTER_LINEAR, B200DR_BOUNDARY_CLAMP>(p, blocks, stream);               \
+        else                                                                            FN<-1, -1>(p, blocks, stream);                                                    \
+    } while (0)
+static void launch_fast_fwd(const TexParams& p, unsigned blocks, cudaStream_t stream) { TEX_MODE_DISPATCH(launch_fast_fwd_c); }
+static void launch_fast_grad(const TexParams& p, unsigned blocks, cudaStream_t stream) { TEX_MODE_DISPATCH(launch_fast_grad_c); }
+
 } // namespace
 
 extern "C" long long b200dr_texture_mip_info(int texW, int texH, int texD, int C, int max_mip_level, int* offsets, int* max_level)
@@ -1307,12 +1479,7 @@ extern "C" int b200dr_texture_fwd(const float* tex, const float* const* mip_ptrs
         size_t blocks = (groups + (TEX_THREADS / 32) - 1) / (TEX_THREADS / 32);
         size_t bcap = (size_t)b200dr_num_sms() * 12;
         if (blocks > bcap) blocks = bcap;
-        switch (C) {
-        case 1: texture_fwd_fast<1><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
-        case 2: texture_fwd_fast<2><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
-        case 3: texture_fwd_fast<3><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
-        case 4: texture_fwd_fast<4><<<(unsigned)blocks, TEX_THREADS, 0, stream>>>(p); break;
-        }
+        launch_fast_fwd(p, (unsigned)blocks, stream);
         B200DR_CHECK_LAUNCH("texture_fwd()");
         return 0;
     }
@@ -1374,7 +1541,6 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
         }
     }
 
-    { const char* e = getenv("B200DR_TEXDBG"); p.dbg = e ? atoi(e) : 0; }
     if (cube)
     {
         size_t blocks = ((size_t)N * H * W + 255) / 256;
@@ -1394,12 +1560,7 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
         size_t blocks = (groups + per_cta - 1) / per_cta;
         size_t bcap = (size_t)b200dr_num_sms() * 20;
         if (blocks > bcap) blocks = bcap;
-        switch (C) {
-        case 1: texture_grad_fast<1><<<(unsigned)blocks, TEXG_THREADS, 0, stream>>>(p); break;
-        case 2: texture_grad_fast<2><<<(unsigned)blocks, TEXG_THREADS, 0, stream>>>(p); break;
-        case 3: texture_grad_fast<3><<<(unsigned)blocks, TEXG_THREADS, 0, stream>>>(p); break;
-        case 4: texture_grad_fast<4><<<(unsigned)blocks, TEXG_THREADS, 0, stream>>>(p); break;
-        }
+        launch_fast_grad(p, (unsigned)blocks, stream);
     }
     else
     {
@@ -1435,3 +1596,13 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
     B200DR_CHECK_LAUNCH("texture_grad(resolve)");
     return 0;
 }
+
+#ifdef TEX_COUNT_HITS
+extern "C" int b200dr_debug_tex_counters(unsigned long long* out8, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, g_tex_counters, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_tex_counters, z, sizeof(z)); }
+    return 0;
+}
+#endif

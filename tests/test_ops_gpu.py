@@ -272,6 +272,39 @@ def test_texture_vs_oracle(dr, filter_mode, boundary_mode, use_da, use_bias, C):
             assert_close(tbias.grad.cpu().numpy(), g["g_bias"], 1e-4, 1e-3, "g_bias", max_bad_frac=5e-3)
 
 
+@pytest.mark.parametrize("filter_mode,boundary_mode", [("linear", "wrap"), ("linear-mipmap-linear", "wrap"), ("linear-mipmap-linear", "clamp"),
+                                                       ("linear-mipmap-nearest", "zero"), ("nearest", "wrap")])
+@pytest.mark.parametrize("texD", [1, 2])
+def test_texture_uniform_regions(dr, filter_mode, boundary_mode, texD):
+    """Images with large constant-uv regions (background) interleaved with varying ones: exercises the per-warp
+    uniform-group result cache and the pending texel-gradient sums of the fast kernels (hit, miss, refill with another
+    constant, per-slice keys for minibatched textures, ragged tail)."""
+    rng = np.random.default_rng(33)
+    N, H, W, C = 2, 67, 129, 3                                    # N*H*W not a multiple of 32
+    tex = rng.uniform(size=(texD, 32, 32, C)).astype(np.float32)
+    uv = rng.uniform(-0.2, 1.2, size=(N, H, W, 2)).astype(np.float32)
+    uv_da = (rng.normal(size=(N, H, W, 4)) * 0.02).astype(np.float32)
+    for n, (r0, r1, cu_, cda) in enumerate([(0, 30, (0.0, 0.0), 0.0), (20, 67, (0.37, 0.81), 0.0)]):
+        uv[n, r0:r1] = cu_; uv_da[n, r0:r1] = cda
+    uv[0, 40:55] = (0.5, 0.25); uv_da[0, 40:55] = (0.03, 0.0, 0.0, 0.03)        # uniform AND minified (two mip levels)
+    uv[1, 5:12] = (0.0, 0.0); uv_da[1, 5:12] = 0.0                              # same constant as image 0, other slice
+    mip = "mipmap" in filter_mode
+    ttex = cu(tex).requires_grad_(True); tuv = cu(uv).requires_grad_(True)
+    tda = cu(uv_da).requires_grad_(True) if mip else None
+    out = dr.texture(ttex, tuv, tda, filter_mode=filter_mode, boundary_mode=boundary_mode)
+    oo = oracle.texture_fwd(tex, uv, uv_da if mip else None, None, filter_mode=filter_mode, boundary_mode=boundary_mode)
+    assert_close(out.detach().cpu().numpy(), oo, 2e-5, 1e-4, "tex out", max_bad_frac=2e-3)
+    dy = _rand_like(out.shape, 34)
+    dy[0, 10:14] = 0.0                                                          # inactive pixels inside a uniform region
+    (out * cu(dy)).sum().backward()
+    g = oracle.texture_grad(tex, uv, dy, uv_da if mip else None, None, filter_mode=filter_mode, boundary_mode=boundary_mode)
+    assert_grad_close(ttex.grad.cpu().numpy(), g["g_tex"], 2e-3, "g_tex")
+    if filter_mode != "nearest":
+        assert_close(tuv.grad.cpu().numpy(), g["g_uv"], 1e-3, 1e-3, "g_uv", max_bad_frac=5e-3)
+    if filter_mode == "linear-mipmap-linear":
+        assert_close(tda.grad.cpu().numpy(), g["g_uv_da"], 1e-3, 2e-3, "g_uv_da", max_bad_frac=5e-3)
+
+
 def test_texture_mip_stack_and_wrapper(dr):
     rng = np.random.default_rng(18)
     tex = rng.uniform(size=(1, 16, 32, 3)).astype(np.float32)
