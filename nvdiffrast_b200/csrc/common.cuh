@@ -335,4 +335,28 @@ static __device__ __forceinline__ void red_add4(float* p, float4 v)
     asm volatile("red.global.v4.f32.add [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// ---- TMA bulk copy (1-D, global -> shared) with an mbarrier transaction count: cp.async.bulk / UBLKCP on sm_100a.
+// dst, src 16-byte aligned, bytes a multiple of 16.  One thread issues; every consumer waits on the barrier's phase.
+static __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+static __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+static __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    uint32_t ok;
+    do
+    {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 #endif // __CUDACC__

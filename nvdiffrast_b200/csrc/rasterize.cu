@@ -31,7 +31,7 @@ struct RastParams
     float           vxs, vxo, vys, vyo;     // clip-space remap into the viewport: x' = x*vxs + w*vxo (impl/RasterImpl.cpp:295-298)
     int             instance_mode;
     int             max_tris;       // per image
-    int             cap;            // record slots per image (7 * max_tris)
+    int             cap;            // record slots per image (7 * max_tris, rounded up to even)
     const uint32_t* peel_in;
     uint32_t*       depth_out;
     // BINS scratch
@@ -407,8 +407,10 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
 {
     __shared__ BinTri   s_tri[BIN_LIST];            // 16 KB
     __shared__ int      s_idx[BIN_IDX];             //  8 KB
-    __shared__ uint32_t s_ids[BIN_SIZE * BIN_SIZE]; // 16 KB
+    __shared__ __align__(16) uint32_t s_ids[BIN_SIZE * BIN_SIZE]; // 16 KB; during the scan: staging buffer of one bbox segment
+    __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ int      s_count;
+    uint2* const s_bb = (uint2*)s_ids;              // BIN_IDX bounding boxes = 16 KB, filled by a TMA bulk copy per segment
 
     const int tid = threadIdx.x;
     const int n = blockIdx.z;
@@ -451,14 +453,24 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
     bool any = false;
     // Records are scanned in segments of BIN_IDX records (the index list cannot overflow); within a segment the scan loop
     // has no barrier: every thread tests bounding boxes and appends the indices of this bin's triangles to s_idx.
+    if (tid == 0) mbar_init(&s_mbar, 1);
+    uint32_t phase = 0;
     for (int seg = 0; seg < total; seg += BIN_IDX)
     {
-        if (tid == 0) s_count = 0;
-        __syncthreads();
         const int seg_end = min(seg + BIN_IDX, total);
+        if (tid == 0)
+        {
+            s_count = 0;
+            // one TMA bulk copy brings the segment's bounding boxes into shared memory (cap is even, so the source is
+            // 16-byte aligned; an odd count is rounded up and reads one slot of the same array that is then ignored)
+            tma_load_1d(s_bb, bboxes + seg, (uint32_t)(((seg_end - seg) * 8 + 15) & ~15), &s_mbar);
+        }
+        __syncthreads();
+        mbar_wait(&s_mbar, phase);
+        phase ^= 1u;
         for (int i = seg + tid; i < seg_end; i += BIN_THREADS)
         {
-            uint2 bb = __ldg(bboxes + i);
+            uint2 bb = s_bb[i - seg];
             int x0 = (int)(bb.x & 0xFFFFu), x1 = (int)(bb.x >> 16), y0 = (int)(bb.y & 0xFFFFu), y1 = (int)(bb.y >> 16);
             if (x0 <= binX1 && x1 >= binX0 && y0 <= binY1 && y1 >= binY0 && x0 <= x1)
                 s_idx[atomicAdd(&s_count, 1)] = i;
@@ -475,7 +487,7 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
             for (int j = tid; j < cnt; j += BIN_THREADS)        // bin-relative edge / depth setup, one triangle per thread
             {
                 int i = s_idx[lb + j];
-                uint2 bb = __ldg(bboxes + i);
+                uint2 bb = s_bb[i - seg];
                 int x0 = (int)(bb.x & 0xFFFFu), x1 = (int)(bb.x >> 16), y0 = (int)(bb.y & 0xFFFFu), y1 = (int)(bb.y >> 16);
                 uint4 ra = __ldg(recs + i * 2), rb = __ldg(recs + i * 2 + 1);
                 int ax = s16lo(ra.x), ay = s16hi(ra.x), bx = s16lo(ra.y), by = s16hi(ra.y), cx = s16lo(ra.z), cy = s16hi(ra.z);
@@ -941,7 +953,7 @@ extern "C" size_t b200dr_rasterize_scratch_bytes(int N, int max_tris, int H, int
     if (path == B200DR_RAST_AUTO) path = b200dr_rasterize_pick_path(N, max_tris, H, W);
     if (path == B200DR_RAST_BINS)
     {
-        size_t cap = (size_t)7 * max_tris;
+        size_t cap = ((size_t)7 * max_tris + 1) & ~(size_t)1;   // even: every image's bbox array stays 16-byte aligned (TMA bulk copies)
         return align_up((size_t)N * sizeof(int), 256) + align_up((size_t)N * cap * sizeof(uint2), 256) + (size_t)N * cap * 2 * sizeof(uint4);
     }
     return (size_t)N * H * W * sizeof(unsigned long long);
@@ -971,7 +983,7 @@ extern "C" int b200dr_rasterize_fwd(const float* pos, const int32_t* tri, const 
     RastParams p = {};
     p.pos = pos; p.tri = tri; p.ranges = ranges_dev;
     p.N = N; p.V = V; p.T = T; p.H = H; p.W = W; p.instance_mode = instance_mode; p.max_tris = max_tris;
-    p.cap = 7 * max_tris;
+    p.cap = (7 * max_tris + 1) & ~1;
     p.peel_in = peel_depth_in; p.depth_out = depth_out;
     p.rast = rast; p.rast_db = rast_db;
     p.xs = 2.f / (float)W; p.xo = 1.f / (float)W - 1.f;

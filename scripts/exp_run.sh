@@ -4,7 +4,7 @@ run() {
   python -c "
 import json; d=json.load(open('gpurun_out/b_var.json')); o=d['ops']; print('$1', round(d['ms_per_step'],3), 'e2e', d.get('e2e',{}).get('ms_per_step'), ' '.join('%s=%.3f'%(k.replace('rasterize','ras').replace('interpolate','ip').replace('texture','tex').replace('antialias','aa'),v['ms']) for k,v in o.items() if v['ms']>0.1))" || tail -5 gpurun_out/b_var.err
 }
+timeout 60 python -m pytest tests/test_ops_gpu.py -m gpu -x -q -k "rasterize_vs_oracle and triangle" 2>&1 | tail -3
 timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 run base "" ""
-B200DR_RG_SMEM=0 run nosmem "" --no-e2e
 for f in nvdiffrast_b200/variants/*.so; do n=$(basename $f .so); run ${n#libb200dr_} $PWD/$f --no-e2e; done
