@@ -349,6 +349,16 @@ static __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// several copies under one transaction count: mbar_expect_tx(total bytes) once, then tma_copy_1d per piece
+static __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void tma_copy_1d(void* dst, const void* src, uint32_t bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 static __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
 {
     uint32_t ok;

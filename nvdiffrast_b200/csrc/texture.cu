@@ -122,27 +122,18 @@ static __device__ __forceinline__ void mip_level_from(const TexParams& p, const 
     level0 = 0; level1 = 0; flevel = 0.f;
     if (m.filter == B200DR_FILTER_NEAREST || m.filter == B200DR_FILTER_LINEAR) return;
     float fl = 0.f;
+    float uscl = 0.f, vscl = 0.f, dsdx = 0.f, dsdy = 0.f, dtdx = 0.f, dtdy = 0.f, A = 0.f, B = 0.f, Cc = 0.f, l2a = 0.f, l2b = 0.f, l2n = 0.f;
     if (m.has_da)
     {
-        float uscl = (float)p.texW, vscl = (float)p.texH;
-        float dsdx = q.x * uscl, dsdy = q.y * uscl, dtdx = q.z * vscl, dtdy = q.w * vscl;
-        float A = dsdx * dsdx + dtdx * dtdx;
-        float B = dsdy * dsdy + dtdy * dtdy;
-        float Cc = dsdx * dsdy + dtdx * dtdy;
-        float l2b = 0.5f * (A + B);
-        float l2n = 0.25f * (A - B) * (A - B) + Cc * Cc;
-        float l2a = sqrtf(l2n);
-        float lenMajorSqr = l2b + l2a;
-        if (WANT_DW && m.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR)
-        {
-            float d = __fdividef(0.72134752f, l2n + l2a * l2b);      // 0.5 / ln 2; gradient-only quantity: approximate division (2 ulp)
-            float AB = d * .5f * (A - B), Cw = d * Cc, l2aw = d * l2a;
-            float4 r = make_float4(uscl * (dsdx * (l2aw + AB) + dsdy * Cw), uscl * (dsdy * (l2aw - AB) + dsdx * Cw),
-                                   vscl * (dtdx * (l2aw + AB) + dtdy * Cw), vscl * (dtdy * (l2aw - AB) + dtdx * Cw));
-            bool fin = isfinite(r.x) && isfinite(r.y) && isfinite(r.z) && isfinite(r.w);
-            dw = fin ? r : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        fl = .5f * __log2f(lenMajorSqr);
+        uscl = (float)p.texW; vscl = (float)p.texH;
+        dsdx = q.x * uscl; dsdy = q.y * uscl; dtdx = q.z * vscl; dtdy = q.w * vscl;
+        A = dsdx * dsdx + dtdx * dtdx;
+        B = dsdy * dsdy + dtdy * dtdy;
+        Cc = dsdx * dsdy + dtdx * dtdy;
+        l2b = 0.5f * (A + B);
+        l2n = 0.25f * (A - B) * (A - B) + Cc * Cc;
+        l2a = sqrtf(l2n);
+        fl = .5f * __log2f(l2b + l2a);
     }
     if (m.has_bias) fl += bias;
     fl = fminf(fmaxf(fl, 0.f), (float)p.mip_max);
@@ -153,6 +144,17 @@ static __device__ __forceinline__ void mip_level_from(const TexParams& p, const 
         fl -= (float)level0;
     }
     flevel = fl;
+    // d(level)/d(uv_da) only ever multiplies the difference between the two levels' samples, which exists only when the
+    // pixel blends two levels (flevel > 0): skipped for magnified / single-level pixels.
+    if (WANT_DW && m.has_da && m.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && flevel > 0.f)
+    {
+        float d = __fdividef(0.72134752f, l2n + l2a * l2b);      // 0.5 / ln 2; gradient-only quantity: approximate division (2 ulp)
+        float AB = d * .5f * (A - B), Cw = d * Cc, l2aw = d * l2a;
+        float4 r = make_float4(uscl * (dsdx * (l2aw + AB) + dsdy * Cw), uscl * (dsdy * (l2aw - AB) + dsdx * Cw),
+                               vscl * (dtdx * (l2aw + AB) + dtdy * Cw), vscl * (dtdy * (l2aw - AB) + dtdx * Cw));
+        bool fin = isfinite(r.x) && isfinite(r.y) && isfinite(r.z) && isfinite(r.w);
+        dw = fin ? r : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 }
 
 // one 128-bit load: channels [k, k+4) of texel tc in a Cp-padded level (zeros for tc < 0)
