@@ -253,7 +253,27 @@ def cpu_oracle_rate(workload, res, samples=1):
 # ----------------------------------------------------------------------------------------------
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries (NCCL's version banner, torchrun notices) write to fd 1 behind
+    Python's back, so fd 1 is pointed at stderr for the whole run and the result line goes to a private copy of the
+    original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -277,7 +297,7 @@ def main():
         # reference CUDA build not loadable here: time the CPU oracle on rank 0 instead (bounded sample)
         if rank == 0:
             rate, dt, thr = cpu_oracle_rate(args.workload, res, 1)
-            print(json.dumps({"impl": "reference", "metric": "Mpixels/sec fwd+bwd (rasterize+interpolate+texture+antialias) at %d^2" % res,
+            emit(({"impl": "reference", "metric": "Mpixels/sec fwd+bwd (rasterize+interpolate+texture+antialias) at %d^2" % res,
                               "value": rate, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3,
                               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
                               "config": {"workload": args.workload, "res": res, "note": "CPU oracle port; reference CUDA build unavailable"},
@@ -442,7 +462,7 @@ def main():
         rate, dt, thr = cpu_oracle_rate(args.workload, res, ns)
         out["cpu_baseline"] = {"value": rate, "unit": "Mpixel/s", "cores": thr, "kind": "port",
                                "sample": "%d image(s) %dx%d of the same workload, fwd+bwd, %.1f s" % (ns, res, res, dt)}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         torch.distributed.destroy_process_group()
 
