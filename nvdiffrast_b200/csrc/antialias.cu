@@ -124,13 +124,18 @@ struct AAParams
 // 128 x 16 pixel tile.  All of a thread's loads (AA_ROWS + 1 triangle ids, AA_ROWS colour vectors) are issued before the
 // first use, the "next row" neighbour is the thread's own next register, the right neighbour a shuffle; no shared memory,
 // no block barrier, one atomic per warp for all the work items of its 32 x AA_ROWS pixels.
+#ifndef AA_ROWS
 #define AA_ROWS   8
+#endif
+#ifndef AA_MINB
+#define AA_MINB   1
+#endif
 #define AA_WARPS_X 4
 #define AA_WARPS_Y 2
 #define AA_TILE_W (32 * AA_WARPS_X)
 #define AA_TILE_H (AA_ROWS * AA_WARPS_Y)
 
-__global__ void __launch_bounds__(256) aa_discontinuity_kernel(const AAParams p)
+__global__ void __launch_bounds__(256, AA_MINB) aa_discontinuity_kernel(const AAParams p)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x0 = blockIdx.x * AA_TILE_W + (warp % AA_WARPS_X) * 32;       // first column of this warp

@@ -258,7 +258,9 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_kernel(const Inte
 // known: empty regions cost 16 bytes per pixel instead of the full algorithmic traffic.
 // ================================================================================================
 
+#ifndef IPF_UNROLL
 #define IPF_UNROLL 2
+#endif
 
 template <int A>
 static __device__ __forceinline__ void load_row(const float* a, float (&v)[A])
@@ -483,6 +485,23 @@ static bool fast_ok(const InterpParams& p, bool da, const void* attr)
         case 9: KERNEL<4, true ><<<GRID, IP_THREADS, SMEM, STREAM>>>(P); break;             \
         } } while (0)
 
+// resident CTAs per SM of the fast backward kernel for this (A, DA, dynamic smem): sizes the persistent grid
+static int grad_fast_resident(int A, bool da, size_t smem)
+{
+    int n = 0;
+    switch (A * 2 + (da ? 1 : 0)) {
+    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<1, false>, IP_THREADS, smem); break;
+    case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<1, true >, IP_THREADS, smem); break;
+    case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<2, false>, IP_THREADS, smem); break;
+    case 5: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<2, true >, IP_THREADS, smem); break;
+    case 6: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<3, false>, IP_THREADS, smem); break;
+    case 7: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<3, true >, IP_THREADS, smem); break;
+    case 8: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<4, false>, IP_THREADS, smem); break;
+    case 9: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<4, true >, IP_THREADS, smem); break;
+    }
+    return n > 0 ? n : 1;
+}
+
 static int fill_params(InterpParams& p, const char* fn, const float* attr, const float* rast, const int32_t* tri, const float* rast_db,
                        int N, int H, int W, int V, int T, int A, int attr_bc, int instance_mode,
                        int diff_all, const int32_t* diff_list, int n_diff)
@@ -573,9 +592,6 @@ extern "C" int b200dr_interpolate_grad(const float* attr, const float* rast, con
         size_t smem_f = stage_b + (p.use_smem_acc ? acc_b : 0);
         int groups = (int)(((size_t)H * W + 31) / 32);
         int gx = (groups + (IP_THREADS / 32) * IPF_UNROLL - 1) / ((IP_THREADS / 32) * IPF_UNROLL);
-        int capx = ((p.use_smem_acc ? b200dr_num_sms() * 4 : b200dr_num_sms() * 12) + N - 1) / N;
-        if (gx > capx) gx = capx;
-        if (gx < 1) gx = 1;
         if (smem_f > 48 * 1024)
         {
             switch (A * 2 + (da ? 1 : 0)) {
@@ -589,6 +605,11 @@ extern "C" int b200dr_interpolate_grad(const float* attr, const float* rast, con
             case 9: cudaFuncSetAttribute(interpolate_grad_fast<4, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
             }
         }
+        // shared accumulators: exactly the resident wave (every CTA zeroes and flushes V*A sums once), rounded DOWN so that no
+        // CTA is left over for a second wave; global accumulation: a few waves
+        int capx = p.use_smem_acc ? max(b200dr_num_sms() * grad_fast_resident(A, da, smem_f) / N, 1) : (b200dr_num_sms() * 12 + N - 1) / N;
+        if (gx > capx) gx = capx;
+        if (gx < 1) gx = 1;
         IP_DISPATCH(interpolate_grad_fast, A, da, dim3(gx, N), smem_f, stream, p);
         B200DR_CHECK_LAUNCH("interpolate_grad()");
         return 0;

@@ -844,11 +844,16 @@ static __device__ __forceinline__ void raster_grad_pixel(const RastGradParams& p
     g[6] = gp2x; g[7] = gp2y; g[8] = gp2w;
 }
 
+#ifndef RG_UNROLL
 #define RG_UNROLL 2
+#endif
+#ifndef RG_MINB
+#define RG_MINB 4
+#endif
 
 // Warp-autonomous: a warp owns groups of 32 consecutive pixels of image blockIdx.y, two groups in flight.
 template <bool ENABLE_DB>
-__global__ void __launch_bounds__(256, 4) raster_grad_kernel(const RastGradParams p)
+__global__ void __launch_bounds__(256, RG_MINB) raster_grad_kernel(const RastGradParams p)
 {
     extern __shared__ float s_acc[];
     const int n = blockIdx.y;
@@ -1075,8 +1080,8 @@ extern "C" int b200dr_rasterize_grad(const float* pos, const int32_t* tri, const
     size_t smem = (size_t)V * 4 * sizeof(float);
     p.use_smem = (smem <= 64 * 1024) ? 1 : 0;
     // Persistent-ish grid: enough CTAs to fill the machine, few enough that the shared-memory flush stays negligible.
-    int target = b200dr_num_sms() * 4;
-    int gx = p.use_smem ? (target + N - 1) / N : 16384;
+    int target = b200dr_num_sms() * RG_MINB;
+    int gx = p.use_smem ? max(target / N, 1) : 16384;       // shared accumulators: one resident wave, rounded down
     int max_gx = (p.chunks + RG_UNROLL - 1) / RG_UNROLL;        // 256-pixel chunks = 8 warp groups per CTA pass
     if (gx > max_gx) gx = max_gx;
     if (gx < 1) gx = 1;

@@ -4,8 +4,5 @@ run() {
   python -c "
 import json; d=json.load(open('gpurun_out/b_var.json')); o=d['ops']; print('$1', round(d['ms_per_step'],3), 'e2e', d.get('e2e',{}).get('ms_per_step'), ' '.join('%s=%.3f'%(k.replace('rasterize','ras').replace('interpolate','ip').replace('texture','tex').replace('antialias','aa'),v['ms']) for k,v in o.items() if v['ms']>0.1))" || tail -5 gpurun_out/b_var.err
 }
-timeout -k 5 120 python -m pytest tests/test_ops_gpu.py -m gpu -x -q -k "texture" 2>&1 | tail -3
-timeout -k 5 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout -k 5 100 python scripts/tex_uniform_bench.py
 run base "" --no-e2e
 for f in $(ls nvdiffrast_b200/variants/*.so 2>/dev/null); do n=$(basename $f .so); run ${n#libb200dr_} $PWD/$f --no-e2e; done
