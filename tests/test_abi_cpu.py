@@ -64,3 +64,44 @@ def test_ops_refuse_cpu_tensors():
         dr.interpolate(torch.zeros(3, 2), torch.zeros(1, 4, 4, 4), torch.zeros(1, 3, dtype=torch.int32))
     with pytest.raises(RuntimeError):
         dr.antialias_construct_topology_hash(torch.zeros(4, 3, dtype=torch.int32))
+
+
+def test_c_abi_rejects_bad_arguments_before_touching_the_device():
+    """Argument validation of the C entry points runs on the host before any launch: error code + message, no GPU needed.
+    (Mirrors the NVDR_CHECK preconditions of csrc/torch/torch_*.cpp.)"""
+    from nvdiffrast_b200 import _lib
+    lib = _lib.load()
+    vp = ctypes.c_void_p
+    err = lambda: lib.b200dr_last_error().decode()
+    ptrs = (vp * 17)()
+    # texture: unsupported modes, empty shapes, mipmapping without uv_da / bias, cube restrictions
+    base = dict(tex=vp(256), uv=vp(256), N=1, H=4, W=4, D=1, Ht=8, Wt=8, C=3)
+    def tex_fwd(filter_mode, boundary_mode, uv_da=None, bias=None, **kw):
+        a = dict(base); a.update(kw)
+        return lib.b200dr_texture_fwd(a["tex"], ptrs, 0, a["uv"], uv_da, bias, a["N"], a["H"], a["W"], a["D"], a["Ht"], a["Wt"], a["C"],
+                                      filter_mode, boundary_mode, vp(256), None)
+    assert tex_fwd(7, 1) != 0 and "filter_mode unsupported" in err()
+    assert tex_fwd(1, 9) != 0 and "boundary_mode unsupported" in err()
+    assert tex_fwd(1, 1, N=0) != 0 and "uv must have shape" in err()
+    assert tex_fwd(1, 1, C=0) != 0 and "tex must have shape" in err()
+    assert tex_fwd(1, 1, D=2, N=3) != 0 and "minibatch size mismatch" in err()
+    assert tex_fwd(3, 1) != 0 and "requires uv_da and/or mip_level_bias" in err()
+    assert tex_fwd(1, 0, C=5) != 0 and "at most 4 channels" in err()
+    assert tex_fwd(1, 0, Ht=8, Wt=16) != 0 and "square in cube map mode" in err()
+    assert tex_fwd(1, 1, uv=vp(260)) != 0 and "not aligned" in err()
+    # rasterize
+    def rast_fwd(**kw):
+        a = dict(pos=vp(256), tri=vp(256), ranges=None, N=1, V=3, T=1, H=16, W=16, inst=1, max_tris=1, scratch=vp(256), sbytes=1 << 20, path=1,
+                 rast=vp(256), db=vp(256)); a.update(kw)
+        return lib.b200dr_rasterize_fwd(a["pos"], a["tri"], a["ranges"], a["N"], a["V"], a["T"], a["H"], a["W"], a["inst"], a["max_tris"], None, None,
+                                        a["scratch"], a["sbytes"], a["path"], a["rast"], a["db"], None)
+    assert rast_fwd(T=0) != 0 and "non-empty" in err()
+    assert rast_fwd(H=0) != 0 and "resolution" in err()
+    assert rast_fwd(inst=0) != 0 and "range mode requires ranges" in err()
+    assert rast_fwd(pos=vp(260)) != 0 and "not aligned to float4" in err()
+    assert rast_fwd(path=5) != 0 and "invalid path" in err()
+    assert rast_fwd(sbytes=8) != 0 and "scratch buffer too small" in err()
+    assert rast_fwd(N=70000, sbytes=1 << 40) != 0
+    # antialias topology
+    assert lib.b200dr_antialias_construct_topology(vp(256), 0, 3, vp(256), vp(256), 1 << 20, None) != 0 and "tri must have shape" in err()
+    assert lib.b200dr_antialias_construct_topology(vp(256), 4, 3, vp(256), vp(256), 8, None) != 0 and "scratch buffer too small" in err()
