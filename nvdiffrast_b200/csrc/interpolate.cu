@@ -258,6 +258,9 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_kernel(const Inte
 // known: empty regions cost 16 bytes per pixel instead of the full algorithmic traffic.
 // ================================================================================================
 
+#ifndef ACC_SMEM_MAX_V
+#define ACC_SMEM_MAX_V (1 << 30)
+#endif
 #ifndef IPF_UNROLL
 #define IPF_UNROLL 2
 #endif
@@ -588,7 +591,7 @@ extern "C" int b200dr_interpolate_grad(const float* attr, const float* rast, con
     {
         size_t stage_b = (size_t)(IP_THREADS / 32) * 32 * ((A == 3) ? (da ? 6 : 3) : 1) * sizeof(float);
         size_t acc_b = (size_t)V * A * sizeof(float);
-        p.use_smem_acc = (acc_b + stage_b <= 64 * 1024) ? 1 : 0;
+        p.use_smem_acc = (acc_b + stage_b <= 64 * 1024 && V <= ACC_SMEM_MAX_V) ? 1 : 0;
         size_t smem_f = stage_b + (p.use_smem_acc ? acc_b : 0);
         int groups = (int)(((size_t)H * W + 31) / 32);
         int gx = (groups + (IP_THREADS / 32) * IPF_UNROLL - 1) / ((IP_THREADS / 32) * IPF_UNROLL);

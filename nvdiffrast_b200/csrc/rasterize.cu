@@ -844,6 +844,10 @@ static __device__ __forceinline__ void raster_grad_pixel(const RastGradParams& p
     g[6] = gp2x; g[7] = gp2y; g[8] = gp2w;
 }
 
+// Shared-memory gradient accumulators pay a CAS loop per fp32 add; they win only while few vertices make global reductions collide.
+#ifndef ACC_SMEM_MAX_V
+#define ACC_SMEM_MAX_V (1 << 30)
+#endif
 #ifndef RG_UNROLL
 #define RG_UNROLL 2
 #endif
@@ -1078,7 +1082,7 @@ extern "C" int b200dr_rasterize_grad(const float* pos, const int32_t* tri, const
     size_t hw = (size_t)H * W;
     p.chunks = (int)((hw + 255) / 256);
     size_t smem = (size_t)V * 4 * sizeof(float);
-    p.use_smem = (smem <= 64 * 1024) ? 1 : 0;
+    p.use_smem = (smem <= 64 * 1024 && V <= ACC_SMEM_MAX_V) ? 1 : 0;
     // Persistent-ish grid: enough CTAs to fill the machine, few enough that the shared-memory flush stays negligible.
     int target = b200dr_num_sms() * RG_MINB;
     int gx = p.use_smem ? max(target / N, 1) : 16384;       // shared accumulators: one resident wave, rounded down
