@@ -66,6 +66,7 @@ int    b200dr_rasterize_pick_path(int N, int max_tris_per_image, int H, int W);
  *   peel_depth_in  NULL, or previous layer's depth [N,H,W] (fragments with depth <= it are killed;
  *                  impl/FineRaster.inl:349)
  *   depth_out      NULL, or receives this layer's depth [N,H,W] (needed only by DepthPeeler)
+ *   scratch        b200dr_rasterize_scratch_bytes() bytes, 16-byte aligned, need not be initialised
  *   rast, rast_db  [N,H,W,4] outputs
  */
 int b200dr_rasterize_fwd(const float* pos, const int32_t* tri, const int32_t* ranges_dev,

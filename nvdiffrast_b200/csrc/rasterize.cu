@@ -986,6 +986,7 @@ extern "C" int b200dr_rasterize_fwd(const float* pos, const int32_t* tri, const 
     if (path == B200DR_RAST_AUTO) path = b200dr_rasterize_pick_path(N, max_tris, H, W);
     B200DR_CHECK(path == B200DR_RAST_BINS || path == B200DR_RAST_SCATTER, "rasterize_fwd(): invalid path");
     B200DR_CHECK(scratch && scratch_bytes >= b200dr_rasterize_scratch_bytes(N, max_tris, H, W, path), "rasterize_fwd(): scratch buffer too small");
+    B200DR_CHECK(B200DR_ALIGNED16(scratch), "rasterize_fwd(): scratch buffer not 16-byte aligned");      // TMA bulk copies read the bbox arrays
     B200DR_CHECK(N <= 65535, "rasterize_fwd(): minibatch size above 65535 is not supported");
     B200DR_CHECK(!peel_depth_in || depth_out, "rasterize_fwd(): peeling needs a depth output buffer");
 
