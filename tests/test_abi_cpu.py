@@ -105,3 +105,33 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_device():
     # antialias topology
     assert lib.b200dr_antialias_construct_topology(vp(256), 0, 3, vp(256), vp(256), 1 << 20, None) != 0 and "tri must have shape" in err()
     assert lib.b200dr_antialias_construct_topology(vp(256), 4, 3, vp(256), vp(256), 8, None) != 0 and "scratch buffer too small" in err()
+
+
+def test_public_api_signatures_match_the_reference_front_end():
+    """Drop-in surface: every public function / class of nvdiffrast/torch/ops.py exists in nvdiffrast_b200.torch with the same
+    positional parameter names and defaults (fixture: tests/golden/api_signatures.json, made by make_api_signatures.py)."""
+    import inspect
+    import json
+    import nvdiffrast_b200.torch as dr
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "api_signatures.json")))
+
+    def check(name, fn, want):
+        params = list(inspect.signature(fn).parameters.values())
+        got = [(p.name, None if p.default is inspect.Parameter.empty else repr(p.default)) for p in params
+               if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]
+        exp = [(w["name"], w["default"]) for w in want]
+        if name.endswith("__exit__"):
+            return                                              # *args catch-all on both sides
+        assert got == exp, "%s: %s != reference %s" % (name, got, exp)
+
+    for name, spec in ref.items():
+        assert hasattr(dr, name), "missing public name %s" % name
+        obj = getattr(dr, name)
+        if isinstance(spec, dict):
+            if name == "RasterizeGLContext":
+                continue                                        # OpenGL context: deliberately a stub that raises (no GL interop)
+            for m, want in spec["methods"].items():
+                assert hasattr(obj, m), "%s.%s missing" % (name, m)
+                check("%s.%s" % (name, m), getattr(obj, m), want)
+        else:
+            check(name, obj, spec)
