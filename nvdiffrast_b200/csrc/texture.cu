@@ -30,6 +30,7 @@ struct TexParams
     int filter, boundary, mip_max;
     int staged;
     int chunks;                             // 256-pixel chunks over the flat N*H*W pixel array
+    int tile2d, tilesX, tilesPerImg;        // TEXG_TILE2D experiment: a warp's 32 pixels form an 8x4 tile instead of a row segment
 };
 
 static __device__ __forceinline__ int lvl_w(const TexParams& p, int l) { int v = p.texW >> l; return v > 1 ? v : 1; }
@@ -557,12 +558,49 @@ static __device__ __forceinline__ void uni_store_key(UniKey* slot, float2 uv, fl
     *(uint4*)&slot->k[4] = make_uint4(__float_as_uint(da.z), __float_as_uint(da.w), __float_as_uint(bias), (unsigned)tz);
 }
 
+// Pixel of lane `lane` in group g.  Default: 32 consecutive pixels of the flat image array.  With TEXG_TILE2D (round-2
+// experiment, off by default, needs W % 8 == 0 and H % 4 == 0): an 8x4 pixel tile, so that neighbouring lanes share texel
+// quads in both directions (fewer distinct sectors per tap instruction, longer merge runs).
+#ifndef TEXG_TILE2D
+#define TEXG_TILE2D 0
+#endif
+static __device__ __forceinline__ size_t group_pixel(const TexParams& p, size_t g, int lane)
+{
+#if TEXG_TILE2D
+    if (p.tile2d)
+    {
+        unsigned t = (unsigned)g, n = t / (unsigned)p.tilesPerImg, r = t - n * (unsigned)p.tilesPerImg;
+        unsigned ty = r / (unsigned)p.tilesX, tx = r - ty * (unsigned)p.tilesX;
+        return ((size_t)n * p.H + ty * 4 + (lane >> 3)) * p.W + tx * 8 + (lane & 7);
+    }
+#endif
+    return g * 32 + lane;
+}
+
 #ifndef TEXF_UNROLL
 #define TEXF_UNROLL 2
 #endif
 #ifndef TEXF_MINB
 #define TEXF_MINB 4
 #endif
+
+// one group's [32][C] output rows: warp-cooperative 128-bit stores (row segment) or per-lane stores (8x4 tile)
+template <int C>
+static __device__ __forceinline__ void tex_store_out(const TexParams& p, size_t g, size_t pidx, const float (&o)[C], int lane, bool inb, bool full, float* stage)
+{
+#if TEXG_TILE2D
+    if (p.tile2d)
+    {
+        if (inb)
+        {
+            #pragma unroll
+            for (int i = 0; i < C; i++) p.out[pidx * C + i] = o[i];
+        }
+        return;
+    }
+#endif
+    warp_store_aos<C>(p.out + g * 32 * C, o, lane, inb, full, stage);
+}
 
 template <int C, int F, int B>
 __global__ void __launch_bounds__(TEX_THREADS, TEXF_MINB) texture_fwd_fast(const TexParams p)
@@ -587,7 +625,7 @@ __global__ void __launch_bounds__(TEX_THREADS, TEXF_MINB) texture_fwd_fast(const
         #pragma unroll
         for (int u = 0; u < TEXF_UNROLL; u++)
         {
-            size_t pidx = (g0 + u * wstride) * 32 + lane;
+            size_t pidx = group_pixel(p, g0 + u * wstride, lane);
             inb[u] = (g0 + u * wstride < groups) && (pidx < total);
             uv[u] = make_float2(0.f, 0.f); da[u] = make_float4(0.f, 0.f, 0.f, 0.f); bias[u] = 0.f;
             if (inb[u])
@@ -602,7 +640,7 @@ __global__ void __launch_bounds__(TEX_THREADS, TEXF_MINB) texture_fwd_fast(const
         {
             size_t g = g0 + u * wstride;
             if (g >= groups) continue;                  // warp-uniform
-            size_t pidx = g * 32 + lane;
+            size_t pidx = group_pixel(p, g, lane);
             const bool full = (g * 32 + 32 <= total);
             const int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
             float o[C];
@@ -610,7 +648,7 @@ __global__ void __launch_bounds__(TEX_THREADS, TEXF_MINB) texture_fwd_fast(const
             {
                 TEX_COUNT(0);
                 unpack4<C>(s_val[warp], o);
-                warp_store_aos<C>(p.out + g * 32 * C, o, lane, true, true, s_stage[warp]);
+                tex_store_out<C>(p, g, pidx, o, lane, true, true, s_stage[warp]);
                 continue;
             }
             TEX_COUNT(1);
@@ -637,7 +675,7 @@ __global__ void __launch_bounds__(TEX_THREADS, TEXF_MINB) texture_fwd_fast(const
                 }
             }
             unpack4<C>(r, o);
-            warp_store_aos<C>(p.out + g * 32 * C, o, lane, inb[u], full, s_stage[warp]);
+            tex_store_out<C>(p, g, pidx, o, lane, inb[u], full, s_stage[warp]);
             if (full && uni_identical(uv[u], da[u], bias[u], tz))
             {
                 TEX_COUNT(2);
@@ -701,13 +739,14 @@ static __device__ __forceinline__ void pending_flush(Pending<C>& pd, const TexPa
 
 // Streaming inputs of one 32-pixel group, loaded up front (two groups are in flight per warp).
 template <int C>
-struct TexGradIn { AosRaw<C> dy; float2 uv; float4 da; float bias; bool inb, full; size_t g; };
+struct TexGradIn { AosRaw<C> dy; float2 uv; float4 da; float bias; bool inb, full; size_t g, pidx; };
 
 template <int C>
 static __device__ __forceinline__ void texgrad_issue(const TexParams& p, const TexMode& m, size_t g, size_t groups, size_t total, int lane, TexGradIn<C>& in)
 {
     in.g = g;
-    size_t pidx = g * 32 + lane;
+    size_t pidx = group_pixel(p, g, lane);
+    in.pidx = pidx;
     in.inb = (g < groups) && (pidx < total);
     in.full = (g < groups) && (g * 32 + 32 <= total);
     in.uv = make_float2(0.f, 0.f); in.da = make_float4(0.f, 0.f, 0.f, 0.f); in.bias = 0.f;
@@ -717,6 +756,21 @@ static __device__ __forceinline__ void texgrad_issue(const TexParams& p, const T
         if (m.has_da) in.da = ld_stream_f4((const float4*)p.uv_da + pidx);
         if (m.has_bias) in.bias = ld_stream_f(p.bias + pidx);
     }
+#if TEXG_TILE2D
+    if (p.tile2d)
+    {
+        in.dy.q[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in.inb)
+        {
+            const float* d = p.dy + pidx * C;
+            in.dy.q[0].x = ld_stream_f(d);
+            if (C > 1) in.dy.q[0].y = ld_stream_f(d + 1 % C);
+            if (C > 2) in.dy.q[0].z = ld_stream_f(d + 2 % C);
+            if (C > 3) in.dy.q[0].w = ld_stream_f(d + 3 % C);
+        }
+        return;
+    }
+#endif
     warp_load_aos_issue<C>(p.dy + g * 32 * C, in.dy, lane, in.inb, in.full);
 }
 
@@ -737,9 +791,13 @@ template <int C, int B>
 static __device__ __forceinline__ void texgrad_group(const TexParams& p, const TexMode& m, const TexGradIn<C>& in, Pending<C>& pd, bool& cached,
                                                      UniGradSlot* slot, int lane, float* sw, size_t hw, bool trilinear)
 {
-    const size_t pidx = in.g * 32 + lane;
+    const size_t pidx = in.pidx;
     const bool inb = in.inb;
     float dy[C];
+#if TEXG_TILE2D
+    if (p.tile2d) unpack4<C>(in.dy.q[0], dy);
+    else
+#endif
     warp_load_aos_finish<C>(p.dy + in.g * 32 * C, in.dy, dy, lane, inb, in.full, sw);
     const float2 uv = in.uv;
     const int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
@@ -1348,6 +1406,8 @@ static int tex_fill(TexParams& p, const char* fn, const float* tex, const float*
     size_t total = (size_t)N * H * W;
     B200DR_CHECK(total < (1ull << 31) * 128, "%s: too many pixels", fn);
     p.chunks = (int)((total + TEX_THREADS - 1) / TEX_THREADS);
+    p.tile2d = (TEXG_TILE2D && (W % 8) == 0 && (H % 4) == 0) ? 1 : 0;
+    p.tilesX = W / 8; p.tilesPerImg = (W / 8) * (H / 4);
     return 0;
 }
 
