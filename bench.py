@@ -83,6 +83,13 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
+        if not self.samples:                             # the polling loop produced nothing in time: one direct query
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=20)
+                self.samples = [l.strip() for l in r.stdout.splitlines() if l.strip()]
+            except Exception:
+                pass
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for s in self.samples:
