@@ -135,3 +135,25 @@ def test_public_api_signatures_match_the_reference_front_end():
                 check("%s.%s" % (name, m), getattr(obj, m), want)
         else:
             check(name, obj, spec)
+
+
+def test_header_is_plain_c_and_the_c_example_links():
+    """The boundary is a C ABI: include/b200dr.h compiles as C99 and examples/c_abi_triangle.c links against the library
+    with nothing but the CUDA runtime (no torch, no C++)."""
+    import shutil
+    import subprocess
+    import tempfile
+    from nvdiffrast_b200 import _lib
+    _lib.load()
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "b200dr.h")
+    subprocess.check_call([gcc, "-std=c99", "-fsyntax-only", "-x", "c", hdr])
+    cuda = "/usr/local/cuda"
+    if not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("CUDA toolkit headers not found")
+    with tempfile.TemporaryDirectory() as tmp:
+        subprocess.check_call([gcc, "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+                               os.path.join(ROOT, "examples", "c_abi_triangle.c"), "-o", os.path.join(tmp, "t"),
+                               "-L", os.path.dirname(_lib.so_path()), "-lb200dr", "-L", os.path.join(cuda, "lib64"), "-lcudart"])
