@@ -349,13 +349,33 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_fwd_fast(const InterpP
     }
 }
 
+// Round-2 experiment (off by default): IPG_FIXED=1 keeps the shared-memory copy of g_attr as 64-bit fixed point (2^-32
+// resolution), so that an add is one native shared-memory integer atomic instead of an fp32 compare-and-swap loop and the
+// per-CTA sums become order-independent; costs twice the shared memory.
+#ifndef IPG_FIXED
+#define IPG_FIXED 0
+#endif
+static __device__ __forceinline__ void acc_add(float* a, float v, bool smem)
+{
+#if IPG_FIXED
+    if (smem)
+    {
+        atomicAdd((unsigned long long*)a, (unsigned long long)__float2ll_rn(v * 4294967296.f));
+        return;
+    }
+#endif
+    (void)smem;
+    red_add(a, v);
+}
+
 template <int A, bool DA>
 __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const InterpParams p)
 {
     extern __shared__ __align__(16) float s_dyn[];
     constexpr int SK = (A == 3) ? (DA ? 6 : 3) : 1;
     float* s_stage = s_dyn;                                             // [8 warps][32 * SK]
-    float* s_acc = s_dyn + (IP_THREADS / 32) * 32 * SK;                 // [V * A] when use_smem_acc
+    float* s_acc = s_dyn + (IP_THREADS / 32) * 32 * SK;                 // [V * A] when use_smem_acc (IPG_FIXED: [V * A] 64-bit words)
+    constexpr int AW = IPG_FIXED ? 2 : 1;                               // floats per shared accumulator
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.y;
     const int hw = p.H * p.W;
@@ -372,7 +392,7 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const Interp
 
     if (p.use_smem_acc)
     {
-        for (int i = tid; i < acc_n; i += IP_THREADS) s_acc[i] = 0.f;
+        for (int i = tid; i < acc_n * AW; i += IP_THREADS) s_acc[i] = 0.f;
         __syncthreads();
     }
 
@@ -420,9 +440,10 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const Interp
                 load_row<A>(p.attr + (size_t)vi2 * A, a2);
                 WarpRuns runs = warp_runs(valid ? float_to_triidx(r[u].w) : -1);
                 bool head = runs.is_head && valid;
-                float* ga0 = acc + (size_t)(vi0 - voff) * A;
-                float* ga1 = acc + (size_t)(vi1 - voff) * A;
-                float* ga2 = acc + (size_t)(vi2 - voff) * A;
+                const int aw = p.use_smem_acc ? AW : 1;
+                float* ga0 = acc + (size_t)(vi0 - voff) * A * aw;
+                float* ga1 = acc + (size_t)(vi1 - voff) * A * aw;
+                float* ga2 = acc + (size_t)(vi2 - voff) * A * aw;
                 float b0 = r[u].x, b1 = r[u].y, b2 = 1.f - r[u].x - r[u].y;
                 #pragma unroll
                 for (int i = 0; i < A; i++)
@@ -441,7 +462,7 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const Interp
                         t0 += du; t1 += dv; t2 += -du - dv;
                     }
                     t0 = warp_run_sum(t0, runs); t1 = warp_run_sum(t1, runs); t2 = warp_run_sum(t2, runs);
-                    if (head) { red_add(ga0 + i, t0); red_add(ga1 + i, t1); red_add(ga2 + i, t2); }
+                    if (head) { acc_add(ga0 + i * aw, t0, p.use_smem_acc); acc_add(ga1 + i * aw, t1, p.use_smem_acc); acc_add(ga2 + i * aw, t2, p.use_smem_acc); }
                 }
                 if (!valid) { gr = make_float4(0.f, 0.f, 0.f, 0.f); gdb = gr; }
             }
@@ -458,7 +479,11 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const Interp
         __syncthreads();
         for (int i = tid; i < acc_n; i += IP_THREADS)
         {
+#if IPG_FIXED
+            float v = (float)((double)((const long long*)s_acc)[i] * (1.0 / 4294967296.0));
+#else
             float v = s_acc[i];
+#endif
             if (v != 0.f) red_add(gbase + i, v);
         }
     }
@@ -590,7 +615,7 @@ extern "C" int b200dr_interpolate_grad(const float* attr, const float* rast, con
     if (fast_ok(p, da, attr) && B200DR_ALIGNED16(dy) && (!da || (((uintptr_t)dda) & 31) == 0))
     {
         size_t stage_b = (size_t)(IP_THREADS / 32) * 32 * ((A == 3) ? (da ? 6 : 3) : 1) * sizeof(float);
-        size_t acc_b = (size_t)V * A * sizeof(float);
+        size_t acc_b = (size_t)V * A * sizeof(float) * (IPG_FIXED ? 2 : 1);
         p.use_smem_acc = (acc_b + stage_b <= 64 * 1024 && V <= ACC_SMEM_MAX_V) ? 1 : 0;
         size_t smem_f = stage_b + (p.use_smem_acc ? acc_b : 0);
         int groups = (int)(((size_t)H * W + 31) / 32);
