@@ -848,6 +848,9 @@ static __device__ __forceinline__ void raster_grad_pixel(const RastGradParams& p
 #ifndef ACC_SMEM_MAX_V
 #define ACC_SMEM_MAX_V (1 << 30)
 #endif
+#ifndef RG_COND_LOADS
+#define RG_COND_LOADS 0
+#endif
 #ifndef RG_UNROLL
 #define RG_UNROLL 2
 #endif
@@ -886,10 +889,26 @@ __global__ void __launch_bounds__(256, RG_MINB) raster_grad_kernel(const RastGra
             if (inb[u])
             {
                 ro[u] = ld_stream_f4((const float4*)p.rast + img + r);
+#if !RG_COND_LOADS
+                dy[u] = ld_stream_f2((const float2*)p.dy + (img + r) * 2);
+                if (ENABLE_DB) ddb[u] = ld_stream_f4((const float4*)p.ddb + img + r);
+#endif
+            }
+        }
+#if RG_COND_LOADS
+        // round-2 experiment (off by default): incoming gradients are fetched only under geometry (empty pixels then cost
+        // 16 instead of 40-48 bytes); the extra dependency runs in parallel with the triangle -> vertex gathers
+        #pragma unroll
+        for (int u = 0; u < RG_UNROLL; u++)
+        {
+            int r = (g0 + u * wstride) * 32 + lane;
+            if (inb[u] && ro[u].w != 0.f)
+            {
                 dy[u] = ld_stream_f2((const float2*)p.dy + (img + r) * 2);
                 if (ENABLE_DB) ddb[u] = ld_stream_f4((const float4*)p.ddb + img + r);
             }
         }
+#endif
         #pragma unroll
         for (int u = 0; u < RG_UNROLL; u++)
         {
