@@ -10,6 +10,7 @@
 //     triangle ids with the right/up neighbours and appends work items with one atomic per warp;
 //   * position gradients are summed per run of equal (triangle, edge) inside the warp before the atomics.
 #include "common.cuh"
+#include "pixel_math.cuh"
 
 namespace {
 
@@ -220,19 +221,6 @@ __global__ void __launch_bounds__(256, AA_MINB) aa_discontinuity_kernel(const AA
 // ------------------------------------------------------------------------------------------------
 // Sparse pass: silhouette analysis and blending (csrc/common/antialias.cu:219-382).
 
-static __device__ __forceinline__ bool same_sign(float a, float b) { return (__float_as_int(a) ^ __float_as_int(b)) >= 0; }
-static __device__ __forceinline__ bool rational_gt(float n0, float n1, float d0, float d1) { return (n0 * d1 > n1 * d0) == same_sign(d0, d1); }
-static __device__ __forceinline__ int max_idx3(float n0, float n1, float n2, float d0, float d1, float d2)
-{
-    bool g10 = rational_gt(n1, n0, d1, d0);
-    bool g20 = rational_gt(n2, n0, d2, d0);
-    bool g21 = rational_gt(n2, n1, d2, d1);
-    if (g20 && g21) return 2;
-    if (g10) return 1;
-    return 0;
-}
-#define AA_F32_MAX (3.402823466e+38f)
-
 __global__ void __launch_bounds__(256) aa_analysis_kernel(const AAParams p)
 {
     const int count = min(p.counters[0], 2 * p.N * p.H * p.W);
@@ -255,66 +243,23 @@ __global__ void __launch_bounds__(256) aa_analysis_kernel(const AAParams p)
         if (tri == tri1) { px += 1 - d; py += d; }
         if (tri < 0 || tri >= p.T) continue;
 
-        int vi0, vi1, vi2;
-        if (!load_tri(p.tri, tri, p.V, vi0, vi1, vi2)) continue;
-        int4 wg = __ldg(p.wings + tri);
-        int op0 = wg.x, op1 = wg.y, op2 = wg.z;
-        if (p.instance_mode)
+        int vi[3];
+        if (!load_tri(p.tri, tri, p.V, vi[0], vi[1], vi[2])) continue;
+        const int4 wg = __ldg(p.wings + tri);
+        const int wv[3] = { wg.x, wg.y, wg.z };
+        const float4* vb = (const float4*)p.pos + (p.instance_mode ? (size_t)pz * p.V : 0);
+        float4 vtx[3], wing[3];
+        #pragma unroll
+        for (int i = 0; i < 3; i++) vtx[i] = __ldg(vb + vi[i]);
+        #pragma unroll
+        for (int i = 0; i < 3; i++) wing[i] = (wv[i] < 0) ? vtx[i] : __ldg(vb + wv[i]);   // open edge: counts as a silhouette
+
+        const pm::AAEdgeResult r = pm::aa_edge(vtx, wing, px, py, p.xh, p.yh, d != 0, tri == tri0);
+        if (r.blend)
         {
-            int vbase = pz * p.V;
-            vi0 += vbase; vi1 += vbase; vi2 += vbase;
-            if (op0 >= 0) op0 += vbase;
-            if (op1 >= 0) op1 += vbase;
-            if (op2 >= 0) op2 += vbase;
-        }
-        const float4* vb = (const float4*)p.pos;
-        float4 p0 = __ldg(vb + vi0), p1 = __ldg(vb + vi1), p2 = __ldg(vb + vi2);
-        float4 o0 = (op0 < 0) ? p0 : __ldg(vb + op0);
-        float4 o1 = (op1 < 0) ? p1 : __ldg(vb + op1);
-        float4 o2 = (op2 < 0) ? p2 : __ldg(vb + op2);
-
-        // to pixel space, relative to the chosen pixel's centre
-        float w0 = 1.f / p0.w, w1 = 1.f / p1.w, w2 = 1.f / p2.w;
-        float ow0 = 1.f / o0.w, ow1 = 1.f / o1.w, ow2 = 1.f / o2.w;
-        float fx = (float)px + .5f - p.xh;
-        float fy = (float)py + .5f - p.yh;
-        float x0 = p0.x * w0 * p.xh - fx, y0 = p0.y * w0 * p.yh - fy;
-        float x1 = p1.x * w1 * p.xh - fx, y1 = p1.y * w1 * p.yh - fy;
-        float x2 = p2.x * w2 * p.xh - fx, y2 = p2.y * w2 * p.yh - fy;
-        float ox0 = o0.x * ow0 * p.xh - fx, oy0 = o0.y * ow0 * p.yh - fy;
-        float ox1 = o1.x * ow1 * p.xh - fx, oy1 = o1.y * ow1 * p.yh - fy;
-        float ox2 = o2.x * ow2 * p.xh - fx, oy2 = o2.y * ow2 * p.yh - fy;
-
-        // silhouette test: a wing on the same side as the triangle itself
-        float bb = (x1 - x0) * (y2 - y0) - (x2 - x0) * (y1 - y0);
-        float a0 = (x1 - ox0) * (y2 - oy0) - (x2 - ox0) * (y1 - oy0);
-        float a1 = (x2 - ox1) * (y0 - oy1) - (x0 - ox1) * (y2 - oy1);
-        float a2 = (x0 - ox2) * (y1 - oy2) - (x1 - ox2) * (y0 - oy2);
-        if (!(same_sign(a0, bb) || same_sign(a1, bb) || same_sign(a2, bb))) continue;
-
-        if (d) { float t; t = x0; x0 = y0; y0 = t; t = x1; x1 = y1; y1 = t; t = x2; x2 = y2; y2 = t; }
-        float dx0 = x2 - x1, dx1 = x0 - x2, dx2 = x1 - x0;
-        float dy0 = y2 - y1, dy1 = y0 - y2, dy2 = y1 - y0;
-
-        float dc = -AA_F32_MAX;
-        float ds = (tri == tri0) ? 1.f : -1.f;
-        float d0 = ds * (x1 * dy0 - y1 * dx0);
-        float d1 = ds * (x2 * dy1 - y2 * dx1);
-        float d2 = ds * (x0 * dy2 - y0 * dx2);
-        if (same_sign(y1, y2)) { d0 = -AA_F32_MAX; dy0 = 1.f; }
-        if (same_sign(y2, y0)) { d1 = -AA_F32_MAX; dy1 = 1.f; }
-        if (same_sign(y0, y1)) { d2 = -AA_F32_MAX; dy2 = 1.f; }
-
-        int di = max_idx3(d0, d1, d2, dy0, dy1, dy2);
-        if (di == 0 && same_sign(a0, bb) && fabsf(dy0) >= fabsf(dx0)) dc = d0 / dy0;
-        if (di == 1 && same_sign(a1, bb) && fabsf(dy1) >= fabsf(dx1)) dc = d1 / dy1;
-        if (di == 2 && same_sign(a2, bb) && fabsf(dy2) >= fabsf(dx2)) dc = d2 / dy2;
-        const float eps = .0625f;
-
-        if (dc > -eps && dc < 1.f + eps)
-        {
-            dc = fminf(fmaxf(dc, 0.f), 1.f);
-            float alpha = ds * (.5f - dc);
+            const float alpha = r.alpha;
+            const int di = r.edge;
+            const float ds = (tri == tri0) ? 1.f : -1.f;
             const float* c0 = p.color + (size_t)pixel0 * p.C;
             const float* c1 = p.color + (size_t)pixel1 * p.C;
             float* o = p.out + (size_t)(alpha > 0.f ? pixel0 : pixel1) * p.C;
@@ -400,39 +345,9 @@ __global__ void __launch_bounds__(256) aa_grad_kernel(const AAParams p)
         float g[6] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
         if (active)
         {
-            float4 p1 = __ldg((const float4*)p.pos + vi1);
-            float4 p2 = __ldg((const float4*)p.pos + vi2);
-            float pxh = p.xh, pyh = p.yh;
-            float fx = (float)px + .5f - pxh;
-            float fy = (float)py + .5f - pyh;
-            if (d)
-            {
-                float t;
-                t = p1.x; p1.x = p1.y; p1.y = t;
-                t = p2.x; p2.x = p2.y; p2.y = t;
-                t = pxh; pxh = pyh; pyh = t;
-                t = fx; fx = fy; fy = t;
-            }
-            float w1 = 1.f / p1.w, w2 = 1.f / p2.w;
-            float x1 = p1.x * w1 * pxh - fx, y1 = p1.y * w1 * pyh - fy;
-            float x2 = p2.x * w2 * pxh - fx, y2 = p2.y * w2 * pyh - fy;
-            float dx = x2 - x1, dy = y2 - y1;
-            float db = x1 * dy - y1 * dx;
-
-            float ep = copysignf(1e-3f, dy);
-            float iy = 1.f / (dy + ep);
-            float dby = db * iy;
-            float iw1 = -w1 * iy * dd;
-            float iw2 =  w2 * iy * dd;
-            float gp1x = iw1 * pxh * y2;
-            float gp2x = iw2 * pxh * y1;
-            float gp1y = iw1 * pyh * (dby - x2);
-            float gp2y = iw2 * pyh * (dby - x1);
-            float gp1w = -(p1.x * gp1x + p1.y * gp1y) * w1;
-            float gp2w = -(p2.x * gp2x + p2.y * gp2y) * w2;
-            if (d) { float t; t = gp1x; gp1x = gp1y; gp1y = t; t = gp2x; gp2x = gp2y; gp2y = t; }
-            if (fabsf(alpha) >= 0.5f) { gp1x = gp1y = gp1w = 0.f; gp2x = gp2y = gp2w = 0.f; }
-            g[0] = gp1x; g[1] = gp1y; g[2] = gp1w; g[3] = gp2x; g[4] = gp2y; g[5] = gp2w;
+            float g1[3], g2[3];
+            pm::aa_edge_grad(__ldg((const float4*)p.pos + vi1), __ldg((const float4*)p.pos + vi2), px, py, p.xh, p.yh, d != 0, alpha, dd, g1, g2);
+            g[0] = g1[0]; g[1] = g1[1]; g[2] = g1[2]; g[3] = g2[0]; g[4] = g2[1]; g[5] = g2[2];
         }
 
         // consecutive items often hit the same edge (same two vertices): sum such runs before the atomics

@@ -15,6 +15,7 @@
 // Snapping, culling, clipping, fill rule and the fixed-point depth plane reproduce the reference bit for bit
 // (see oracle/oracle.c for the scalar restatement with citations).
 #include "common.cuh"
+#include "pixel_math.cuh"
 
 namespace {
 
@@ -244,51 +245,17 @@ static __device__ __forceinline__ bool fetch_triangle(const RastParams& p, int n
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pixel shader (csrc/common/rasterize.cu:15-114).  Same expression shapes as the reference so that the compiler's
-// FMA contraction matches to within an ulp.
+// Pixel shader: replaces RasterizeCudaFwdShaderKernel (csrc/common/rasterize.cu:15-114).  The arithmetic lives in
+// pixel_math.cuh (pm::pixel_tri + pm::shade), shared with the backward kernel and executable on the host for the tests.
 
 static __device__ __forceinline__ void shade_pixel(const RastParams& p, int n, int triIdx, int px, int py, float4& o, float4& db)
 {
-    int vi0 = __ldg(p.tri + triIdx * 3 + 0), vi1 = __ldg(p.tri + triIdx * 3 + 1), vi2 = __ldg(p.tri + triIdx * 3 + 2);
     const float4* vb = (const float4*)p.pos + (p.instance_mode ? (size_t)n * p.V : 0);
-    float4 p0 = __ldg(vb + vi0), p1 = __ldg(vb + vi1), p2 = __ldg(vb + vi2);
-
-    float fx = p.xs * (float)px + p.xo;
-    float fy = p.ys * (float)py + p.yo;
-    float p0x = p0.x - fx * p0.w, p0y = p0.y - fy * p0.w;
-    float p1x = p1.x - fx * p1.w, p1y = p1.y - fy * p1.w;
-    float p2x = p2.x - fx * p2.w, p2y = p2.y - fy * p2.w;
-    float a0 = p1x * p2y - p1y * p2x;
-    float a1 = p2x * p0y - p2y * p0x;
-    float a2 = p0x * p1y - p0y * p1x;
-
-    float iw = 1.f / (a0 + a1 + a2);
-    float b0 = a0 * iw;
-    float b1 = a1 * iw;
-    float z = p0.z * a0 + p1.z * a1 + p2.z * a2;
-    float w = p0.w * a0 + p1.w * a1 + p2.w * a2;
-    float zw = z / w;
-
-    b0 = __saturatef(b0);
-    b1 = __saturatef(b1);
-    float bs = 1.f / fmaxf(b0 + b1, 1.f);
-    b0 *= bs;
-    b1 *= bs;
-    zw = fmaxf(fminf(zw, 1.f), -1.f);
-    o = make_float4(b0, b1, zw, triidx_to_float(triIdx + 1));
-
-    float dfxdx = p.xs * iw;
-    float dfydy = p.ys * iw;
-    float da0dx = p2.y * p1.w - p1.y * p2.w;
-    float da0dy = p1.x * p2.w - p2.x * p1.w;
-    float da1dx = p0.y * p2.w - p2.y * p0.w;
-    float da1dy = p2.x * p0.w - p0.x * p2.w;
-    float da2dx = p1.y * p0.w - p0.y * p1.w;
-    float da2dy = p0.x * p1.w - p1.x * p0.w;
-    float datdx = da0dx + da1dx + da2dx;
-    float datdy = da0dy + da1dy + da2dy;
-    db = make_float4(dfxdx * (b0 * datdx - da0dx), dfydy * (b0 * datdy - da0dy),
-                     dfxdx * (b1 * datdx - da1dx), dfydy * (b1 * datdy - da1dy));
+    const int32_t* vi = p.tri + triIdx * 3;
+    pm::PixelTri t;
+    pm::pixel_tri(t, __ldg(vb + __ldg(vi)), __ldg(vb + __ldg(vi + 1)), __ldg(vb + __ldg(vi + 2)),
+                  p.xs * (float)px + p.xo, p.ys * (float)py + p.yo);
+    pm::shade(t, p.xs, p.ys, triidx_to_float(triIdx + 1), o, db);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -770,78 +737,20 @@ struct RastGradParams
     float xs, xo, ys, yo;
 };
 
-// Gradient of one pixel w.r.t. the clip-space positions of its triangle (csrc/common/rasterize.cu:160-267).
+// Gradient of one pixel w.r.t. the clip-space positions of its triangle: replaces the per-pixel part of RasterizeGradKernel[Db]
+// (csrc/common/rasterize.cu:119-273); derivation and code in pixel_math.cuh (pm::raster_grad).  g = (x, y, w) per vertex.
 template <bool ENABLE_DB>
 static __device__ __forceinline__ void raster_grad_pixel(const RastGradParams& p, int n, int px, int py, int vi0, int vi1, int vi2,
                                                          float2 dy, float4 ddb, bool has_ddb, float (&g)[9])
 {
     const float4* vb = (const float4*)p.pos + (p.instance_mode ? (size_t)n * p.V : 0);
-    float4 p0 = __ldg(vb + vi0), p1 = __ldg(vb + vi1), p2 = __ldg(vb + vi2);
-
-    float fx = p.xs * (float)px + p.xo;
-    float fy = p.ys * (float)py + p.yo;
-    float p0x = p0.x - fx * p0.w, p0y = p0.y - fy * p0.w;
-    float p1x = p1.x - fx * p1.w, p1y = p1.y - fy * p1.w;
-    float p2x = p2.x - fx * p2.w, p2y = p2.y - fy * p2.w;
-    float a0 = p1x * p2y - p1y * p2x;
-    float a1 = p2x * p0y - p2y * p0x;
-    float a2 = p0x * p1y - p0y * p1x;
-
-    float at = a0 + a1 + a2;
-    float ep = copysignf(1e-6f, at);
-    float iw = 1.f / (at + ep);
-    float b0 = a0 * iw, b1 = a1 * iw;
-
-    float gb0 = dy.x * iw, gb1 = dy.y * iw;
-    float gbb = gb0 * b0 + gb1 * b1;
-    float gp0x = gbb * (p2y - p1y) - gb1 * p2y;
-    float gp1x = gbb * (p0y - p2y) + gb0 * p2y;
-    float gp2x = gbb * (p1y - p0y) - gb0 * p1y + gb1 * p0y;
-    float gp0y = gbb * (p1x - p2x) + gb1 * p2x;
-    float gp1y = gbb * (p2x - p0x) - gb0 * p2x;
-    float gp2y = gbb * (p0x - p1x) + gb0 * p1x - gb1 * p0x;
-    float gp0w = -fx * gp0x - fy * gp0y;
-    float gp1w = -fx * gp1x - fy * gp1y;
-    float gp2w = -fx * gp2x - fy * gp2y;
-
-    if (ENABLE_DB && has_ddb)
-    {
-        float dfxdX = p.xs * iw, dfydY = p.ys * iw;
-        ddb.x *= dfxdX; ddb.y *= dfydY; ddb.z *= dfxdX; ddb.w *= dfydY;
-
-        float da0dX = p1.y * p2.w - p2.y * p1.w, da1dX = p2.y * p0.w - p0.y * p2.w, da2dX = p0.y * p1.w - p1.y * p0.w;
-        float da0dY = p2.x * p1.w - p1.x * p2.w, da1dY = p0.x * p2.w - p2.x * p0.w, da2dY = p1.x * p0.w - p0.x * p1.w;
-        float datdX = da0dX + da1dX + da2dX, datdY = da0dY + da1dY + da2dY;
-
-        float x01 = p0.x - p1.x, x12 = p1.x - p2.x, x20 = p2.x - p0.x;
-        float y01 = p0.y - p1.y, y12 = p1.y - p2.y, y20 = p2.y - p0.y;
-        float w01 = p0.w - p1.w, w12 = p1.w - p2.w, w20 = p2.w - p0.w;
-
-        float a0p1 = fy * p2.x - fx * p2.y, a0p2 = fx * p1.y - fy * p1.x;
-        float a1p0 = fx * p2.y - fy * p2.x, a1p2 = fy * p0.x - fx * p0.y;
-
-        float wdudX = 2.f * b0 * datdX - da0dX, wdudY = 2.f * b0 * datdY - da0dY;
-        float wdvdX = 2.f * b1 * datdX - da1dX, wdvdY = 2.f * b1 * datdY - da1dY;
-
-        float c0  = iw * (ddb.x * wdudX + ddb.y * wdudY + ddb.z * wdvdX + ddb.w * wdvdY);
-        float cx  = c0 * fx - ddb.x * b0 - ddb.z * b1;
-        float cy  = c0 * fy - ddb.y * b0 - ddb.w * b1;
-        float cxy = iw * (ddb.x * datdX + ddb.y * datdY);
-        float czw = iw * (ddb.z * datdX + ddb.w * datdY);
-
-        gp0x += c0 * y12 - cy * w12              + czw * p2y                                               + ddb.w * p2.w;
-        gp1x += c0 * y20 - cy * w20 - cxy * p2y                              - ddb.y * p2.w;
-        gp2x += c0 * y01 - cy * w01 + cxy * p1y  - czw * p0y                 + ddb.y * p1.w                - ddb.w * p0.w;
-        gp0y += cx * w12 - c0 * x12              - czw * p2x                                - ddb.z * p2.w;
-        gp1y += cx * w20 - c0 * x20 + cxy * p2x               + ddb.x * p2.w;
-        gp2y += cx * w01 - c0 * x01 - cxy * p1x  + czw * p0x  - ddb.x * p1.w                + ddb.z * p0.w;
-        gp0w += cy * x12 - cx * y12              - czw * a1p0                               + ddb.z * p2.y - ddb.w * p2.x;
-        gp1w += cy * x20 - cx * y20 - cxy * a0p1              - ddb.x * p2.y + ddb.y * p2.x;
-        gp2w += cy * x01 - cx * y01 - cxy * a0p2 - czw * a1p2 + ddb.x * p1.y - ddb.y * p1.x - ddb.z * p0.y + ddb.w * p0.x;
-    }
-    g[0] = gp0x; g[1] = gp0y; g[2] = gp0w;
-    g[3] = gp1x; g[4] = gp1y; g[5] = gp1w;
-    g[6] = gp2x; g[7] = gp2y; g[8] = gp2w;
+    const float fx = p.xs * (float)px + p.xo, fy = p.ys * (float)py + p.yo;
+    pm::PixelTri t;
+    pm::pixel_tri(t, __ldg(vb + vi0), __ldg(vb + vi1), __ldg(vb + vi2), fx, fy);
+    float gx[3], gy[3], gw[3];
+    pm::raster_grad<ENABLE_DB>(t, fx, fy, p.xs, p.ys, dy.x, dy.y, ddb, has_ddb, gx, gy, gw);
+    #pragma unroll
+    for (int m = 0; m < 3; m++) { g[3 * m] = gx[m]; g[3 * m + 1] = gy[m]; g[3 * m + 2] = gw[m]; }
 }
 
 // Shared-memory gradient accumulators pay a CAS loop per fp32 add; they win only while few vertices make global reductions collide.

@@ -6,16 +6,33 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+# Reference sources with the header's own coalesced-atomics switch forced to its plain-atomicAdd branch
+# (oracle/build_ref.sh): the only reference-computed values of raster g_pos / interpolate g_attr / linear-mode g_tex /
+# antialias g_pos that are not corrupted by the caAtomicAdd race on sm_100a.  Both builds define the pybind module
+# `_nvdiffrast_c` (and register the same C++ types), so a process can load only ONE of them: parity tests import the
+# unmodified build in the pytest process and drive the race-free build in a child process (tests/ref_noca_compare.py).
+REF_NOCA_DIR = os.path.join(ROOT, "oracle", "_ref_noca")
+_loaded_variant = None
 
 
-def load_reference():
-    """Import the unmodified reference (built into oracle/_ref by oracle/build_ref.sh); None if absent/unloadable."""
-    if not os.path.isdir(os.path.join(REF_DIR, "nvdiffrast")):
+def reference_available(variant="stock"):
+    d = REF_DIR if variant == "stock" else REF_NOCA_DIR
+    return os.path.isdir(os.path.join(d, "nvdiffrast"))
+
+
+def load_reference(variant="stock"):
+    """Import the reference built by oracle/build_ref.sh: variant 'stock' = unmodified (oracle/_ref), 'noca' = plain-atomics
+    gradient build (oracle/_ref_noca).  None if absent/unloadable."""
+    global _loaded_variant
+    d = REF_DIR if variant == "stock" else REF_NOCA_DIR
+    if not os.path.isdir(os.path.join(d, "nvdiffrast")):
         return None
-    if REF_DIR not in sys.path:
-        sys.path.insert(0, REF_DIR)
+    assert _loaded_variant in (None, variant), "only one reference build per process (already loaded: %s)" % _loaded_variant
+    if d not in sys.path:
+        sys.path.insert(0, d)
     try:
         import nvdiffrast.torch as ref_dr
+        _loaded_variant = variant
         return ref_dr
     except Exception as e:  # e.g. ABI mismatch on another image
         print("reference not loadable:", e)
