@@ -6,8 +6,12 @@ the linear modes, antialias g_pos) comes out WRONG when the unmodified reference
 (contributions are lost; the macros call __match_any_sync(0xffffffff, ..) after some lanes have returned and touch the
 shared slot without a __syncwarp).  Gradients that do not pass through those macros (g_rast, g_rast_db, g_color, g_uv,
 g_uv_da, g_bias, nearest-mode g_tex) and every forward output agree with the oracle to ~1e-7.  Those four tensors are
-therefore NOT used as pins; they are pinned by float64 autograd / exact finite differences instead
-(tests/test_oracle_cpu.py::test_*_float64_*), and test_reference_atomic_gradients_are_corrupted documents the defect."""
+pinned by the `*_rf` arrays instead: the SAME reference sources compiled with common.h's own plain-atomicAdd branch
+(common.h:246-259, selected by a one-line switch in oracle/build_ref.sh -> oracle/_ref_noca), run on the stored inputs by
+the second pass of tests/golden/make_golden.py after checking that its forward outputs are bitwise those of the
+unmodified build.  Tolerance |g - g_rf|_inf <= 1e-4 |g_rf|_inf.  float64 autograd / exact finite
+differences (tests/test_oracle_cpu.py) stay as an independent second pin, and
+test_reference_atomic_gradients_are_corrupted documents the defect."""
 import numpy as np
 
 import oracle
@@ -31,13 +35,26 @@ def check_oracle_against_golden(g):
         out, out_da = oracle.interpolate_fwd(g["attr"], g["rast"], tri, g["rast_db"], "all")
         assert_close(out, g["ip_out"], 1e-5, 1e-5, "interpolate out")
         assert_close(out_da, g["ip_out_da"], 1e-5, 1e-4, "interpolate out_da")
+        gp = oracle.rasterize_grad(pos, tri, g["rast"], g["dy"], g["ddb"])
+        # 1e-4 everywhere except the 96^2 sphere, whose 5856 triangles are smaller than a pixel: the rast_db
+        # term scales with 1/area^2 and the uncontracted fp32 oracle and the FMA-contracted reference round it differently
+        # (measured 1.01e-4; the CUDA kernels agree with the reference to 6e-7 at full size, tests/test_grad_reference_gpu.py)
+        subpixel = float((g["rast"][..., 3] > 0).sum()) < 4.0 * len(np.unique(g["rast"][..., 3]))     # < 4 pixels per visible triangle
+        assert_grad_close(gp, g["g_pos_rf"], 2e-4 if subpixel else 1e-4, "rasterize g_pos vs race-free reference")
         ga, gr, gdb = oracle.interpolate_grad(g["attr"], g["rast"], tri, g["ip_dy"], g["rast_db"], g["ip_dda"], "all")
+        assert_grad_close(ga, g["ip_g_attr_rf"], 1e-4, "interpolate g_attr vs race-free reference")
         assert_close(gr, g["ip_g_rast"], 1e-5, 1e-4, "interpolate g_rast")
         assert_close(gdb, g["ip_g_rast_db"], 1e-5, 1e-4, "interpolate g_rast_db")
         aa, items = oracle.antialias_fwd(g["color"], g["rast"], pos, tri)
         assert_close(aa, g["aa_out"], 2e-6, 1e-5, "antialias out", max_bad_frac=1e-3, hard_atol=1e-2)
         gc, gpa = oracle.antialias_grad(g["color"], g["rast"], pos, tri, g["aa_dy"], items)
         assert_close(gc, g["aa_g_color"], 1e-5, 1e-4, "antialias g_color", max_bad_frac=1e-3)
+        # Knife edge: an item whose crossing was clamped has |alpha| == 0.5 exactly and receives NO position gradient
+        # (antialias.cu:542-546); an exact 45-degree silhouette through pixel centres (the hypotenuse of triangle.py's
+        # triangle) puts its items within one ulp of that switch, so a last-bit difference flips whole contributions.
+        # That scene (the only one with 3 vertices) is excluded from this pin; the other six are pinned.
+        if g["pos"].shape[1] > 3:
+            assert_grad_close(gpa, g["aa_g_pos_rf"], 1e-4, "antialias g_pos vs race-free reference")
         prev = None
         for layer in range(g["peel_ids"].shape[0]):
             o = oracle.rasterize_fwd(pos, tri, res, peel_depth=prev)
@@ -53,8 +70,9 @@ def check_oracle_against_golden(g):
         out = oracle.texture_fwd(g["tex"], g["uv"], uv_da, bias, **kw)
         assert_close(out, g["out"], 2e-5, 1e-4, "texture out", max_bad_frac=2e-3)
         gr = oracle.texture_grad(g["tex"], g["uv"], g["dy"], uv_da, bias, **kw)
-        if kw["filter_mode"] == "nearest":       # the linear modes' g_tex is corrupted in the reference on sm_100a (see above)
+        if kw["filter_mode"] == "nearest":       # the linear modes' g_tex is corrupted in the unmodified build (see above)
             assert_grad_close(gr["g_tex"], g["g_tex"], 1e-5, "g_tex")
+        assert_grad_close(gr["g_tex"], g["g_tex_rf"], 1e-4, "g_tex vs race-free reference")
         if "g_uv" in g:
             assert_close(gr["g_uv"], g["g_uv"], 1e-3, 1e-3, "g_uv", max_bad_frac=5e-3)
         if "g_uv_da" in g:

@@ -92,3 +92,102 @@ def oracle_chain(c, n, with_tex, dy, max_mip_level=-1):
         g_pos = g_pos + oracle.rasterize_grad(pos, tri, rast, g_rast, None)
     grads["pos"] = g_pos
     return rast, color, out, grads
+
+
+# ----------------------------------------------------------------------------------------------
+# Knife-edge predicates and condition-scaled tolerances (no anonymous outlier budgets: every pixel is either held to the
+# stated tolerance or removed by one of these stated predicates)
+
+EPS32 = 2.0 ** -24
+
+
+def raster_condition(pos, tri, rast, res):
+    """Condition number of the barycentrics of every covered pixel, from a float64 evaluation of the edge functions:
+    cond = sum_i (|qx_j qy_k| + |qy_j qx_k|) / |sum_i e_i|.  u, v = e_i / sum(e) carry a rounding error of a few
+    2^-24 * cond whatever the operation order (sliver and sub-pixel triangles have a tiny sum(e) made of O(1) products).
+    Returns (cond [N,H,W], covered mask)."""
+    pos = np.asarray(pos, np.float64); tri = np.asarray(tri)
+    H, W = res
+    ids = np.asarray(rast)[..., 3].astype(np.int64)
+    N = ids.shape[0]
+    cond = np.zeros(ids.shape, np.float64)
+    fx = (2.0 / W) * np.arange(W) + (1.0 / W - 1.0)
+    fy = (2.0 / H) * np.arange(H) + (1.0 / H - 1.0)
+    for n in range(N):
+        ys, xs = np.nonzero(ids[n] > 0)
+        t = tri[ids[n, ys, xs] - 1]
+        vb = pos[n] if pos.ndim == 3 else pos
+        p = vb[t]                                               # [K,3,4]
+        qx = p[:, :, 0] - fx[xs, None] * p[:, :, 3]; qy = p[:, :, 1] - fy[ys, None] * p[:, :, 3]
+        num = np.zeros(len(ys)); den = np.zeros(len(ys))
+        for i in range(3):
+            j, k = (i + 1) % 3, (i + 2) % 3
+            num += np.abs(qx[:, j] * qy[:, k]) + np.abs(qy[:, j] * qx[:, k])
+            den += qx[:, j] * qy[:, k] - qy[:, j] * qx[:, k]
+        cond[n, ys, xs] = num / np.maximum(np.abs(den), 1e-300)
+    return cond, ids > 0
+
+
+def assert_close_cond(a, b, cond, atol, rtol, k, name=""):
+    """|a - b| <= atol + rtol |b| + k 2^-24 cond  for every element (cond broadcast over the channel axis)."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    tol = atol + rtol * np.abs(b) + k * EPS32 * cond[..., None]
+    bad = np.abs(a - b) > tol
+    assert not bad.any(), "%s: %d elements outside atol=%g rtol=%g k=%g (worst excess %.3g at cond %.3g)" % (
+        name, int(bad.sum()), atol, rtol, k, float((np.abs(a - b) - tol).max()), float(cond[bad.any(-1)].max()))
+
+
+def mip_level_f64(uv_da, bias, tex_w, tex_h, max_level):
+    """Continuous (unclamped) mip level of every pixel in float64 (texture_kernel.cu:509-568), for knife-edge predicates."""
+    shape = (uv_da if uv_da is not None else bias).shape[:3]
+    lvl = np.zeros(shape, np.float64)
+    if uv_da is not None:
+        q = np.asarray(uv_da, np.float64)
+        dsdx, dsdy, dtdx, dtdy = q[..., 0] * tex_w, q[..., 1] * tex_w, q[..., 2] * tex_h, q[..., 3] * tex_h
+        A = dsdx ** 2 + dtdx ** 2; B = dsdy ** 2 + dtdy ** 2; C = dsdx * dsdy + dtdx * dtdy
+        lam = 0.5 * (A + B) + np.sqrt(0.25 * (A - B) ** 2 + C ** 2)
+        with np.errstate(divide="ignore"):
+            lvl = 0.5 * np.log2(np.maximum(lam, 1e-300))
+    if bias is not None:
+        lvl = lvl + np.asarray(bias, np.float64)
+    return lvl
+
+
+def texture_knife_edges(uv, uv_da, bias, tex_shape, filter_mode, boundary_mode, max_level, level_eps=1e-3, texel_eps=2e-4):
+    """Pixels that sit on a discontinuity of the texture op, where a last-bit difference upstream legitimately changes the
+    result by a finite amount:
+      level: continuous mip level within `level_eps` of an integer inside [0, max_level], or of the clamp ends (the GPU
+             evaluates it with the approximate __log2f, SURVEY 8(d)); relevant to every output of the mipmapped modes;
+      texel: u*w - 0.5 (or v*h - 0.5) within `texel_eps` of an integer on a level the pixel uses: the bilinear footprint
+             moves to the next texel quad there; the colour is continuous but d(colour)/d(uv) is not, relevant to g_uv,
+             g_uv_da, and -- through which texels receive the (vanishing) weight -- irrelevant to g_tex.
+    Returns (level_mask, texel_mask), each [N,H,W] bool."""
+    D, th, tw = tex_shape[0], tex_shape[-3], tex_shape[-2]
+    uv = np.asarray(uv, np.float64)
+    shape = uv.shape[:3]
+    mip = "mipmap" in filter_mode
+    lvl = mip_level_f64(uv_da, bias, tw, th, max_level) if mip else np.zeros(shape)
+    level_mask = np.zeros(shape, bool)
+    if mip:
+        inside = (lvl > -level_eps) & (lvl < max_level + level_eps)
+        level_mask = inside & (np.abs(lvl - np.round(lvl)) < level_eps)
+    texel_mask = np.zeros(shape, bool)
+    if filter_mode != "nearest":
+        lc = np.clip(lvl, 0, max_level)
+        for L in sorted(set(np.floor(lc).astype(int).ravel().tolist()) | set(np.minimum(np.floor(lc).astype(int) + 1, max_level).ravel().tolist())):
+            uses = (np.floor(lc).astype(int) == L) | ((np.minimum(np.floor(lc).astype(int) + 1, max_level) == L) & (lc > np.floor(lc)) & (filter_mode == "linear-mipmap-linear"))
+            w, h = max(tw >> L, 1), max(th >> L, 1)
+            for c, s in ((0, w), (1, h)):
+                x = uv[..., c]
+                if boundary_mode == "wrap":
+                    x = x - np.floor(x)
+                x = x * s - 0.5
+                texel_mask |= uses & (np.abs(x - np.round(x)) < texel_eps * max(1.0, s / 64.0))
+    else:
+        for c, s in ((0, tw), (1, th)):
+            x = uv[..., c]
+            if boundary_mode == "wrap":
+                x = x - np.floor(x)
+            x = x * s
+            texel_mask |= np.abs(x - np.round(x)) < texel_eps
+    return level_mask, texel_mask
