@@ -1,19 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- Mpixels/s forward+backward of the differentiable-rasterizer hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 Workload (BASELINE.json): c3 = "Spot-like" bumped sphere (5 856 triangles, 2 930 vertices), 2048x2048, 16 images per GPU,
 full chain rasterize -> interpolate(uv, all pixel differentials) -> texture(trilinear, 1024^2 x3) -> antialias, forward +
-backward, seeded synthetic data (workloads.py).  A step = one such pass over one batch; per-GPU work is fixed (weak scaling);
-for N > 1 the vertex-position gradient of the shared mesh is all-reduced over NCCL every step.
+backward, seeded synthetic data (workloads.py).  A step = one such pass over one batch; per-GPU work is fixed (weak scaling).
+With N > 1 the default workload is c5 (the same chain, 32 images per GPU) and every step all-reduces the gradients of ALL
+shared parameters (texture 12.6 MB + uv + vertices) through nvdiffrast_b200.distributed.SharedGradReducer: the texture
+gradient leaves while interpolate / rasterize backward still run, the small rest in one call at the end.
 
-One JSON line on rank 0.  `value` = whole-job Mpixel/s with inputs resident in HBM; `e2e` = the same metric through the
-public API with the step's inputs copied from pinned host memory and the loss + vertex gradient read back every step;
-`roofline` = algorithmic HBM bytes of the dominant op / its CUDA-event time, against the measured copy peak
-(MEASURED_PEAKS.json); `cpu_baseline` = the CPU oracle (a port of the reference math; the reference has no CPU path) timed
-on one image of the same workload.
+One JSON line on rank 0.  `value` = whole-job Mpixel/s with inputs resident in HBM, averaged over `timed_rounds` rounds of
+exactly K steps each (the rounds run back to back until the timed region is >= 1 s, so that the clock record holds tens
+of samples); `e2e` = the same metric through the public API with the step's inputs copied from pinned host memory and the
+loss + vertex gradient read back every step; `roofline` = algorithmic HBM bytes of the dominant op / its CUDA-event time,
+against the measured copy peak (MEASURED_PEAKS.json); `other_configs` (N = 1 only) = c2, c4 and c5's per-GPU batch with the
+same timing rules and their own clock records; `target_kernels` = interpolate / antialias forward + backward at A = C = 3,
+2048^2 (the north-star's >= 70 % kernels); `cpu_baseline` = the CPU oracle (a port of the reference math; the reference has
+no CPU path) timed on a bounded sample of the same workload.
 """
 import argparse
 import contextlib
@@ -30,14 +35,15 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import workloads as wl  # noqa: E402
-from nvdiffrast_b200.distributed import allreduce_shared_grads  # noqa: E402
+from nvdiffrast_b200.distributed import SharedGradReducer  # noqa: E402
 
 FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
 def measured_traffic():
-    """DRAM bytes per pixel per op from the committed ncu --set full capture (profiles/r01_traffic.json), or {}."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """DRAM bytes per pixel per op from THIS round's ncu --set full capture (profiles/r02_traffic.json, written by
+    scripts/ncu_summary.py from the .ncu-rep files of the same build), or {} -> `traffic: null`."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         return json.load(open(p))
     except Exception:
@@ -128,9 +134,13 @@ def op_bytes(workload, P, A, D, C):
 
 
 class Pipeline:
+    """One workload on one GPU: pinned host inputs, two device input slots (the end-to-end loop double-buffers), the op chain
+    through `mod` (our front end or the reference's, same code), and the shared-gradient exchange."""
+
     def __init__(self, mod, workload, n_img, res, device, seed, tex_res=1024):
         self.mod, self.workload, self.device = mod, workload, device
-        if workload == "c3":
+        self.full = workload in ("c3", "c5")                   # full chain (texture + antialias); c2 / c4: rasterize + interpolate
+        if self.full:
             c = wl.config_c3(n=1, res=res, tex_res=tex_res)
             v = wl.sphere_mesh()[0]
         elif workload == "c2":
@@ -146,15 +156,16 @@ class Pipeline:
             "verts": torch.from_numpy(np.concatenate([v, np.ones((v.shape[0], 1), np.float32)], 1)).pin_memory(),
             "mvp": torch.from_numpy(wl.camera_batch(n_img, seed, far=far)).pin_memory(),
         }
-        if workload == "c3":
+        if self.full:
             self.host["uv"] = torch.from_numpy(c["uv"]).pin_memory()
             self.host["tex"] = torch.from_numpy(c["tex"]).pin_memory()
         else:
             self.host["attr"] = torch.from_numpy(c["attr"]).pin_memory()
+        self.shared = [k for k in ("tex", "uv", "attr", "verts") if k in self.host]      # parameters shared by every image
         self.tri = torch.from_numpy(c["tri"]).to(device)
-        self.uv_idx = torch.from_numpy(c["uv_idx"]).to(device) if workload == "c3" else None
+        self.uv_idx = torch.from_numpy(c["uv_idx"]).to(device) if self.full else None
         self.ctx = mod.RasterizeCudaContext(device)
-        self.topo = mod.antialias_construct_topology_hash(self.tri) if workload == "c3" else None
+        self.topo = mod.antialias_construct_topology_hash(self.tri) if self.full else None
         self.bufs = [{}, {}]
         self.upload(0); self.upload(1)
         self.use(0)
@@ -163,6 +174,7 @@ class Pipeline:
         self.dy = torch.randn((n_img, res, res, C), device=device, generator=g)
         self.grad_host = [torch.empty((v.shape[0], 4), dtype=torch.float32).pin_memory() for _ in range(2)]
         self.loss_host = [torch.empty((1,), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.reducer = SharedGradReducer([(k, self.host[k].shape) for k in self.shared], device)
 
     def h2d_bytes(self):
         return int(sum(t.numel() * t.element_size() for t in self.host.values()))
@@ -186,42 +198,30 @@ class Pipeline:
     def use(self, slot):
         self.dev = dict(self.bufs[slot])
 
-    def step(self, world=1, with_loss=False):
-        """forward + backward (+ all-reduce of the shared vertex gradient).  Returns (loss, vertex grad) on the device.
+    def step(self, with_loss=False):
+        """forward + backward + all-reduce of every shared-parameter gradient.  Returns (loss, dict of reduced gradients).
         with_loss: form the scalar loss sum(out * dy) explicitly (end-to-end runs read it back); otherwise dy is fed
         straight into backward, so the timed region contains the hot path and nothing else."""
         mod = self.mod
-        verts = self.dev["verts"].detach().requires_grad_(True)
-        pos = torch.matmul(verts[None], self.dev["mvp"].transpose(1, 2)).contiguous()      # [n, V, 4] clip space
+        leaves = {k: self.dev[k].detach().requires_grad_(True) for k in self.shared}
+        self.reducer.begin(leaves)
+        pos = torch.matmul(leaves["verts"][None], self.dev["mvp"].transpose(1, 2)).contiguous()      # [n, V, 4] clip space
         rast, db = mod.rasterize(self.ctx, pos, self.tri, self.res)
         if os.environ.get("BENCH_DEBUG"):
             sys.stderr.write("coverage %.4f\n" % float((rast[..., 3] > 0).float().mean()))
-        if self.workload == "c3":
-            texc, texd = mod.interpolate(self.dev["uv"][None], rast, self.uv_idx, rast_db=db, diff_attrs="all")
-            color = mod.texture(self.dev["tex"], texc, texd, filter_mode="linear-mipmap-linear", max_mip_level=9)
+        if self.full:
+            texc, texd = mod.interpolate(leaves["uv"][None], rast, self.uv_idx, rast_db=db, diff_attrs="all")
+            color = mod.texture(leaves["tex"], texc, texd, filter_mode="linear-mipmap-linear", max_mip_level=9)
             out = mod.antialias(color, rast, pos, self.tri, topology_hash=self.topo)
         else:
-            out, _ = mod.interpolate(self.dev["attr"][None], rast, self.tri)
+            out, _ = mod.interpolate(leaves["attr"][None], rast, self.tri)
         if with_loss:
             loss = torch.dot(out.reshape(-1), self.dy.reshape(-1))      # scalar loss <out, dy>: one pass over the image
             loss.backward()
         else:
             loss = None
             out.backward(self.dy)
-        g = verts.grad
-        if world > 1:
-            allreduce_shared_grads([g])
-        return loss, g
-
-    def set_requires_grad(self):
-        for k in ("uv", "tex", "attr"):
-            if k in self.dev:
-                self.dev[k] = self.dev[k].detach().requires_grad_(True)
-
-    def zero_grads(self):
-        for k in ("uv", "tex", "attr"):
-            if k in self.dev and self.dev[k].grad is not None:
-                self.dev[k].grad = None
+        return loss, self.reducer.finish()
 
 
 def load_module(impl):
@@ -244,7 +244,7 @@ def cpu_oracle_rate(workload, res, samples=1):
     import oracle
     from util import oracle_chain
     oracle.build()
-    if workload == "c3":
+    if workload in ("c3", "c5"):
         c = wl.config_c3(n=samples, res=res)
     elif workload == "c2":
         c = wl.config_c2(n=samples, res=res)
@@ -252,7 +252,7 @@ def cpu_oracle_rate(workload, res, samples=1):
         c = wl.config_c4(n=samples, res=res)
     dy = np.random.default_rng(2).normal(size=(samples, res, res, 3)).astype(np.float32)
     t0 = time.perf_counter()
-    oracle_chain(c, samples, workload == "c3", dy, max_mip_level=9)
+    oracle_chain(c, samples, workload in ("c3", "c5"), dy, max_mip_level=9)
     dt = time.perf_counter() - t0
     return samples * res * res / dt / 1e6, dt, oracle.num_threads()
 
@@ -279,6 +279,213 @@ def emit(obj):
     _REAL_STDOUT.flush()
 
 
+DEFAULTS = {"c3": (2048, 16), "c2": (1024, 64), "c4": (2048, 8), "c5": (2048, 32)}
+WORKLOAD_TEXT = {
+    "c3": "c3: Spot-like sphere 5856 tris, %d^2, %d images/GPU, rasterize+interpolate(uv,da)+texture(trilinear 1024^2x3)+antialias fwd+bwd",
+    "c5": "c5: Spot-like sphere 5856 tris, %d^2, %d images/GPU (256 over 8 GPUs), rasterize+interpolate(uv,da)+texture(trilinear 1024^2x3)+antialias fwd+bwd",
+    "c2": "c2: cube 12 tris, %d^2, %d images/GPU, rasterize+interpolate fwd+bwd",
+    "c4": "c4: 1M-triangle sphere, %d^2, %d images/GPU, rasterize+interpolate fwd+bwd"}
+MIN_TIMED_SECONDS = 1.0
+
+
+def sync_all(world):
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(ms, device, world):
+    t = torch.tensor([ms], device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def ops_table(trace, K_total, nbytes, peak):
+    """Per-op CUDA-event times over the timed region -> {op: calls/step, ms, bytes, GB/s, frac}."""
+    ops = {}
+    for name, a, b in trace:
+        d = ops.setdefault(name, [0.0, 0])
+        d[0] += a.elapsed_time(b); d[1] += 1
+    table = {}
+    for name, (tot, cnt) in ops.items():
+        avg = tot / cnt
+        e = {"calls_per_step": cnt / K_total, "ms": avg}
+        if name in nbytes:
+            gbs = nbytes[name] / (avg * 1e-3) / 1e9
+            e.update({"algorithmic_bytes": nbytes[name], "GBps": gbs, "frac": gbs / peak})
+        table[name.replace("b200dr_", "")] = e
+    return table, ops
+
+
+def timed_run(pipe, K, W, world, rank, local, device, impl, min_seconds=MIN_TIMED_SECONDS):
+    """W warm-up steps, then rounds of EXACTLY K steps, each round bracketed by CUDA events on the compute stream (barrier +
+    synchronize on both sides of the whole region), repeated back to back until the region has lasted >= min_seconds so that
+    the 25 ms clock sampler sees tens of samples.  Returns mean ms/step (max over ranks), rounds, clocks, op trace, launches."""
+    for _ in range(W):
+        pipe.step()
+    trace, launches0 = [], 0
+    if impl == "ours":
+        from nvdiffrast_b200 import _lib
+        _lib.set_trace(trace)
+        launches0 = _lib.load().b200dr_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sync_all(world)
+    rounds = []
+    t_start = time.perf_counter()
+    while True:
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            pipe.step()
+        e1.record()
+        e1.synchronize()
+        rounds.append(e0.elapsed_time(e1))
+        go = torch.tensor([1.0 if (time.perf_counter() - t_start) < min_seconds and len(rounds) < 200 else 0.0], device=device)
+        if world > 1:                                           # every rank runs the same number of rounds: rank 0 decides
+            torch.distributed.broadcast(go, 0)
+        if float(go.item()) == 0.0:
+            break
+    sync_all(world)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = 0
+    if impl == "ours":
+        _lib.set_trace(None)
+        launches = int(_lib.load().b200dr_launch_count() - launches0)
+    ms_step = max_over_ranks(sum(rounds) / (K * len(rounds)), device, world)
+    return {"ms_per_step": ms_step, "rounds": len(rounds), "round_ms": [r / K for r in rounds[:16]], "clocks": clocks,
+            "trace": trace, "launches": launches}
+
+
+def e2e_run(pipe, K, world, device):
+    """Double-buffered end-to-end loop: step i+1's inputs travel host->device on a copy stream while step i computes; the
+    loss and the vertex gradient of step i are read back asynchronously and consumed (event wait) while step i+1 is in
+    flight.  All uploads and read-backs happen inside the timed region; rounds of K steps until >= 1 s."""
+    copy_stream = torch.cuda.Stream(device=device)
+    main = torch.cuda.current_stream()
+    ready = [torch.cuda.Event(), torch.cuda.Event()]       # slot uploaded
+    free = [torch.cuda.Event(), torch.cuda.Event()]        # slot no longer read by the compute stream
+    done = [torch.cuda.Event(), torch.cuda.Event()]        # results of the step using this slot are on the host
+
+    def run(steps):
+        for sl in (0, 1):
+            free[sl].record(main)
+        copy_stream.wait_event(free[0])
+        pipe.upload(0, copy_stream); ready[0].record(copy_stream)
+        results = []
+        for i in range(steps):
+            sl = i & 1
+            if i + 1 < steps:
+                copy_stream.wait_event(free[sl ^ 1])
+                pipe.upload(sl ^ 1, copy_stream); ready[sl ^ 1].record(copy_stream)
+            main.wait_event(ready[sl])
+            pipe.use(sl)
+            loss, g = pipe.step(with_loss=True)
+            free[sl].record(main)
+            pipe.loss_host[sl].copy_(loss.detach().reshape(1), non_blocking=True)
+            pipe.grad_host[sl].copy_(g["verts"], non_blocking=True)
+            done[sl].record(main)
+            if i > 0:
+                done[sl ^ 1].synchronize()                 # the caller consumes the previous step's result
+                results.append(float(pipe.loss_host[sl ^ 1][0]))
+        done[(steps - 1) & 1].synchronize()
+        results.append(float(pipe.loss_host[(steps - 1) & 1][0]))
+        return results
+
+    run(2)
+    sync_all(world)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    total_ms, rounds, t_start = 0.0, 0, time.perf_counter()
+    while True:
+        e0.record()
+        losses = run(K)
+        e1.record(); e1.synchronize()
+        assert len(losses) == K and all(np.isfinite(l) for l in losses)
+        total_ms += e0.elapsed_time(e1); rounds += 1
+        go = torch.tensor([1.0 if (time.perf_counter() - t_start) < MIN_TIMED_SECONDS and rounds < 200 else 0.0], device=device)
+        if world > 1:
+            torch.distributed.broadcast(go, 0)
+        if float(go.item()) == 0.0:
+            break
+    sync_all(world)
+    return max_over_ranks(total_ms / (K * rounds), device, world), rounds
+
+
+def side_config(mod, name, K, W, device, peak):
+    """One more BASELINE configuration on this GPU (N = 1 only), same timing rules, own clock record."""
+    res, n_img = DEFAULTS[name]
+    pipe = Pipeline(mod, name, n_img, res, device, seed=0)
+    r = timed_run(pipe, K, W, 1, 0, device.index or 0, device, "ours")
+    P = n_img * res * res
+    A, D, C = (2, 2, 3) if pipe.full else (3, 0, 3)
+    nbytes = op_bytes("c3" if pipe.full else name, P, A, D, C)
+    table, ops = ops_table(r["trace"], K * r["rounds"], nbytes, peak)
+    chain = sum(nbytes[n] * ops[n][1] / (K * r["rounds"]) for n in ops if n in nbytes)
+    out = {"workload": WORKLOAD_TEXT[name] % (res, n_img), "ms_per_step": r["ms_per_step"], "value": P / (r["ms_per_step"] * 1e-3) / 1e6,
+           "unit": "Mpixel/s", "steps": K, "timed_rounds": r["rounds"], "clocks": r["clocks"],
+           "ops": {k: {"ms": v["ms"], "frac": v.get("frac")} for k, v in table.items()},
+           "chain_roofline": {"algorithmic_bytes_per_step": chain, "frac": chain / (r["ms_per_step"] * 1e-3) / 1e9 / peak}}
+    del pipe
+    torch.cuda.empty_cache()
+    return out
+
+
+def target_kernels(mod, device, peak, n_img=16, res=2048):
+    """The north-star's >= 70 % kernels in isolation: interpolate fwd/bwd (A = 3, no pixel differentials) and antialias
+    fwd/bwd (C = 3) on the c3 geometry at 2048^2, timed per C-ABI op with CUDA events, >= 0.5 s per pair."""
+    from nvdiffrast_b200 import _lib
+    c = wl.config_c3(n=1, res=res, tex_res=8)
+    v = wl.sphere_mesh()[0]
+    verts = torch.from_numpy(np.concatenate([v, np.ones((v.shape[0], 1), np.float32)], 1)).to(device)
+    mvp = torch.from_numpy(wl.camera_batch(n_img, 0, far=200.0)).to(device)
+    pos = torch.matmul(verts[None], mvp.transpose(1, 2)).contiguous()
+    tri = torch.from_numpy(c["tri"]).to(device)
+    ctx = mod.RasterizeCudaContext(device)
+    with torch.no_grad():
+        rast, _ = mod.rasterize(ctx, pos, tri, (res, res))
+    g = torch.Generator(device=device); g.manual_seed(7)
+    attr = torch.rand((1, v.shape[0], 3), device=device, generator=g)
+    dy = torch.randn((n_img, res, res, 3), device=device, generator=g)
+    topo = mod.antialias_construct_topology_hash(tri)
+    P = n_img * res * res
+    nbytes = {"b200dr_interpolate_fwd": 28 * P, "b200dr_interpolate_grad": 44 * P, "b200dr_antialias_fwd": 40 * P, "b200dr_antialias_grad": 24 * P}
+
+    def interp():
+        a = attr.detach().requires_grad_(True); r = rast.detach().requires_grad_(True)
+        o, _ = mod.interpolate(a, r, tri)
+        o.backward(dy)
+
+    def aa():
+        col = dy.detach().requires_grad_(True); pp = pos.detach().requires_grad_(True)
+        o = mod.antialias(col, rast, pp, tri, topology_hash=topo)
+        o.backward(dy)
+
+    out = {}
+    sampler = ClockSampler(device.index or 0); sampler.start()
+    for fn in (interp, aa):
+        for _ in range(3):
+            fn()
+        trace = []
+        _lib.set_trace(trace)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); it = 0
+        while time.perf_counter() - t0 < 0.5 or it < 10:
+            fn(); it += 1
+            if it % 10 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        _lib.set_trace(None)
+        table, _ = ops_table(trace, it, nbytes, peak)
+        for k, e in table.items():
+            if "frac" in e:
+                out[k] = {"ms": e["ms"], "bytes_per_pixel": nbytes["b200dr_" + k] // P, "GBps": e["GBps"], "frac": e["frac"], "calls": it}
+    out["clocks"] = sampler.stop()
+    out["config"] = "c3 geometry, %d^2, %d images, A = C = 3, coverage %.3f" % (res, n_img, float((rast[..., 3] > 0).float().mean()))
+    return out
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -286,28 +493,29 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c2", "c4"])
+    ap.add_argument("--workload", default=None, choices=["c3", "c2", "c4", "c5"])
     ap.add_argument("--res", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip other_configs / target_kernels")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    defaults = {"c3": (2048, 16), "c2": (1024, 64), "c4": (2048, 8)}
-    res = args.res or defaults[args.workload][0]
-    n_img = args.batch or defaults[args.workload][1]
+    workload = args.workload or ("c3" if world == 1 else "c5")
+    res = args.res or DEFAULTS[workload][0]
+    n_img = args.batch or DEFAULTS[workload][1]
     K, W = args.steps, max(args.warmup, 3)
 
     mod, kind = load_module(args.impl)
     if args.impl == "reference" and mod is None:
         # reference CUDA build not loadable here: time the CPU oracle on rank 0 instead (bounded sample)
         if rank == 0:
-            rate, dt, thr = cpu_oracle_rate(args.workload, res, 1)
+            rate, dt, thr = cpu_oracle_rate(workload, res, 1)
             emit(({"impl": "reference", "metric": "Mpixels/sec fwd+bwd (rasterize+interpolate+texture+antialias) at %d^2" % res,
                               "value": rate, "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3,
                               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-                              "config": {"workload": args.workload, "res": res, "note": "CPU oracle port; reference CUDA build unavailable"},
+                              "config": {"workload": workload, "res": res, "note": "CPU oracle port; reference CUDA build unavailable"},
                               "cpu_baseline": {"value": rate, "unit": "Mpixel/s", "cores": thr, "kind": "port", "sample": "1 image %dx%d" % (res, res)},
                               "e2e": {"value": rate, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -320,96 +528,19 @@ def main():
         os.environ.setdefault("NCCL_DEBUG", "WARN")
         torch.distributed.init_process_group("nccl", device_id=device)
 
-    pipe = Pipeline(mod, args.workload, n_img, res, device, seed=rank)
-    pipe.set_requires_grad()
+    pipe = Pipeline(mod, workload, n_img, res, device, seed=rank)
     P = n_img * res * res
 
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
     # ---- device-resident timing
-    for _ in range(W):
-        pipe.zero_grads(); pipe.step(world)
-    trace = []
-    launches0 = 0
-    if args.impl == "ours":
-        from nvdiffrast_b200 import _lib
-        _lib.set_trace(trace)
-        launches0 = _lib.load().b200dr_launch_count()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        pipe.zero_grads(); pipe.step(world)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = 0
-    if args.impl == "ours":
-        _lib.set_trace(None)
-        launches = int(_lib.load().b200dr_launch_count() - launches0)
-    t = torch.tensor([ms], device=device)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms = float(t.item())
-    value = world * P * K / (ms * 1e-3) / 1e6
+    r = timed_run(pipe, K, W, world, rank, local, device, args.impl)
+    ms_step = r["ms_per_step"]
+    value = world * P / (ms_step * 1e-3) / 1e6
 
     # ---- end to end: inputs from pinned host memory every step, loss + vertex gradient read back every step
     e2e = None
     if not args.no_e2e:
-        # Double-buffered: step i+1's inputs travel host->device on a copy stream while step i computes; the loss and the
-        # vertex gradient of step i are read back asynchronously and consumed (event wait) while step i+1 is in flight.
-        # All K uploads and K read-backs happen inside the timed region.
-        copy_stream = torch.cuda.Stream(device=device)
-        main = torch.cuda.current_stream()
-        ready = [torch.cuda.Event(), torch.cuda.Event()]       # slot uploaded
-        free = [torch.cuda.Event(), torch.cuda.Event()]        # slot no longer read by the compute stream
-        done = [torch.cuda.Event(), torch.cuda.Event()]        # results of the step using this slot are on the host
-
-        def run_e2e(steps):
-            for sl in (0, 1):
-                free[sl].record(main)
-            copy_stream.wait_event(free[0])
-            pipe.upload(0, copy_stream); ready[0].record(copy_stream)
-            results = []
-            for i in range(steps):
-                sl = i & 1
-                if i + 1 < steps:
-                    copy_stream.wait_event(free[sl ^ 1])
-                    pipe.upload(sl ^ 1, copy_stream); ready[sl ^ 1].record(copy_stream)
-                main.wait_event(ready[sl])
-                pipe.use(sl); pipe.set_requires_grad()
-                loss, g = pipe.step(world, with_loss=True)
-                free[sl].record(main)
-                pipe.loss_host[sl].copy_(loss.detach().reshape(1), non_blocking=True)
-                pipe.grad_host[sl].copy_(g, non_blocking=True)
-                done[sl].record(main)
-                if i > 0:
-                    done[sl ^ 1].synchronize()                 # the caller consumes the previous step's result
-                    results.append(float(pipe.loss_host[sl ^ 1][0]))
-            done[(steps - 1) & 1].synchronize()
-            results.append(float(pipe.loss_host[(steps - 1) & 1][0]))
-            return results
-
-        run_e2e(2)
-        barrier()
-        e0.record()
-        losses = run_e2e(K)
-        e1.record()
-        barrier()
-        assert len(losses) == K and all(np.isfinite(l) for l in losses)
-        ms2 = e0.elapsed_time(e1)
-        t = torch.tensor([ms2], device=device)
-        if world > 1:
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms2 = float(t.item())
-        e2e = {"value": world * P * K / (ms2 * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": ms2 / K,
+        ms2, rounds2 = e2e_run(pipe, K, world, device)
+        e2e = {"value": world * P / (ms2 * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": ms2, "timed_rounds": rounds2,
                "h2d_bytes_per_step": pipe.h2d_bytes(), "d2h_bytes_per_step": pipe.d2h_bytes()}
 
     if rank != 0:
@@ -417,41 +548,31 @@ def main():
             torch.distributed.destroy_process_group()
         return
 
-    out = {"metric": "Mpixels/sec fwd+bwd (rasterize+interpolate+texture+antialias) at %d^2" % res if args.workload == "c3"
-           else "Mpixels/sec fwd+bwd (rasterize+interpolate) at %d^2" % res,
-           "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+    full = pipe.full
+    out = {"metric": ("Mpixels/sec fwd+bwd (rasterize+interpolate+texture+antialias) at %d^2" if full else "Mpixels/sec fwd+bwd (rasterize+interpolate) at %d^2") % res,
+           "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
+           "timed_rounds": r["rounds"], "round_ms_per_step": r["round_ms"],
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-           "config": {"workload": {"c3": "c3: Spot-like sphere 5856 tris, %d^2, %d images/GPU, rasterize+interpolate(uv,da)+texture(trilinear 1024^2x3)+antialias fwd+bwd",
-                                   "c2": "c2: cube 12 tris, %d^2, %d images/GPU, rasterize+interpolate fwd+bwd",
-                                   "c4": "c4: 1M-triangle sphere, %d^2, %d images/GPU, rasterize+interpolate fwd+bwd"}[args.workload] % (res, n_img),
+           "config": {"workload": WORKLOAD_TEXT[workload] % (res, n_img),
                       "global_batch": world * n_img, "pixels_per_step": world * P,
                       "l2": "per-step working set (>= %.1f GB of per-pixel tensors) exceeds the 126 MB L2; no explicit flush" % (P * 32 / 1e9),
-                      "parallelism": "dp%d (batch shard, one NCCL all-reduce of the vertex gradient)" % world},
-           "clocks": clocks}
+                      "parallelism": "dp%d (batch shard; all shared-parameter gradients all-reduced every step: %d bytes per rank, "
+                                     "the texture gradient overlapped with the rest of backward)" % (world, pipe.reducer.bytes_per_step)},
+           "comm_bytes_per_step": pipe.reducer.bytes_per_step if world > 1 else 0,
+           "clocks": r["clocks"]}
     if args.impl == "reference":
         out["impl"] = "reference"
-        out["config"]["reference"] = "unmodified NVlabs/nvdiffrast v0.4.0 CUDA extension built for sm_100a (oracle/_ref), same harness; " \
-                                     "the reference has no CPU path (SURVEY.md F1)"
+        out["reference_note"] = "unmodified NVlabs/nvdiffrast v0.4.0 CUDA extension built for sm_100a (oracle/_ref), same harness; " \
+                                "the reference has no CPU path (SURVEY.md F1)"
     if e2e is not None:
         out["e2e"] = e2e
     if args.impl == "ours":
-        out["gpu_launches"] = launches
-        # per-op CUDA-event times over the timed region
+        out["gpu_launches"] = r["launches"]
         peak, peak_src = hbm_peak()
-        A, D, C = (2, 2, 3) if args.workload == "c3" else (3, 0, 3)
-        nbytes = op_bytes(args.workload, P, A, D, C)
-        ops = {}
-        for name, a, b in trace:
-            d = ops.setdefault(name, [0.0, 0])
-            d[0] += a.elapsed_time(b); d[1] += 1
-        table = {}
-        for name, (tot, cnt) in ops.items():
-            avg = tot / cnt
-            e = {"calls_per_step": cnt / K, "ms": avg}
-            if name in nbytes:
-                gbs = nbytes[name] / (avg * 1e-3) / 1e9
-                e.update({"algorithmic_bytes": nbytes[name], "GBps": gbs, "frac": gbs / peak})
-            table[name.replace("b200dr_", "")] = e
+        A, D, C = (2, 2, 3) if full else (3, 0, 3)
+        nbytes = op_bytes("c3" if full else workload, P, A, D, C)
+        Kt = K * r["rounds"]
+        table, ops = ops_table(r["trace"], Kt, nbytes, peak)
         out["ops"] = table
         dom = max((n for n in ops if n in nbytes), key=lambda n: ops[n][0])
         avg = ops[dom][0] / ops[dom][1]
@@ -461,12 +582,17 @@ def main():
                            "frac": ach / peak, "traffic": (tr["dram_bytes_per_pixel"] * P if tr else None),
                            "traffic_source": (tr.get("source") if tr else None), "peak_source": peak_src,
                            "algorithmic_bytes_per_launch": nbytes[dom], "avg_launch_ms": avg}
-        chain_bytes = sum(nbytes[n] * ops[n][1] / K for n in ops if n in nbytes)
-        out["chain_roofline"] = {"algorithmic_bytes_per_step": chain_bytes, "achieved_GBps": chain_bytes / (ms / K * 1e-3) / 1e9,
-                                 "frac": chain_bytes / (ms / K * 1e-3) / 1e9 / peak}
+        chain_bytes = sum(nbytes[n] * ops[n][1] / Kt for n in ops if n in nbytes)
+        out["chain_roofline"] = {"algorithmic_bytes_per_step": chain_bytes, "achieved_GBps": chain_bytes / (ms_step * 1e-3) / 1e9,
+                                 "frac": chain_bytes / (ms_step * 1e-3) / 1e9 / peak}
+        if world == 1 and not args.no_extras and workload == "c3":
+            del pipe
+            torch.cuda.empty_cache()
+            out["target_kernels"] = target_kernels(mod, device, peak)
+            out["other_configs"] = {name: side_config(mod, name, K, W, device, peak) for name in ("c2", "c4", "c5")}
     if not args.no_cpu_baseline and world == 1:
-        ns = {"c3": 12, "c2": 16, "c4": 1}[args.workload]       # bounded sample: ~10 s of host time
-        rate, dt, thr = cpu_oracle_rate(args.workload, res, ns)
+        ns = {"c3": 12, "c5": 12, "c2": 16, "c4": 1}[workload]       # bounded sample: ~10 s of host time
+        rate, dt, thr = cpu_oracle_rate(workload, res, ns)
         out["cpu_baseline"] = {"value": rate, "unit": "Mpixel/s", "cores": thr, "kind": "port",
                                "sample": "%d image(s) %dx%d of the same workload, fwd+bwd, %.1f s" % (ns, res, res, dt)}
     emit(out)

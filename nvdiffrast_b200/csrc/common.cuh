@@ -335,6 +335,26 @@ static __device__ __forceinline__ void red_add4(float* p, float4 v)
     asm volatile("red.global.v4.f32.add [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// 64-bit vector reduction (global memory only, 8-byte aligned): REDG.E.ADD.F32x2.
+static __device__ __forceinline__ void red_add2(float* p, float2 v)
+{
+    asm volatile("red.global.v2.f32.add [%0], {%1,%2};" :: "l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// ---- L2 prefetch of a contiguous byte range (UBLKPF.L2: no registers, no shared memory, no completion to wait for).
+// Streaming kernels walk their per-pixel tensors with a fixed grid stride, so a warp knows the addresses of its NEXT group
+// while it works on the current one: one elected lane asks L2 to fetch them, and the later demand loads find the lines in
+// L2 (~1/3 of the DRAM latency) instead of stalling the warp on HBM.  addr 16-byte aligned, bytes a multiple of 16.
+#ifndef DR_PREFETCH
+#define DR_PREFETCH 1
+#endif
+static __device__ __forceinline__ void prefetch_l2(const void* addr, uint32_t bytes)
+{
+#if DR_PREFETCH
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(addr), "r"(bytes) : "memory");
+#endif
+}
+
 // ---- TMA bulk copy (1-D, global -> shared) with an mbarrier transaction count: cp.async.bulk / UBLKCP on sm_100a.
 // dst, src 16-byte aligned, bytes a multiple of 16.  One thread issues; every consumer waits on the barrier's phase.
 static __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -299,6 +299,15 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_fwd_fast(const InterpP
             r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (inb[u]) r[u] = ld_stream_f4((const float4*)p.rast + img + px);
         }
+        if (lane == 0)                                  // this warp's next groups: ask L2 for their rast lines now
+        {
+            #pragma unroll
+            for (int u = 0; u < IPF_UNROLL; u++)
+            {
+                const int gn = g0 + (IPF_UNROLL + u) * wstride;
+                if (gn * 32 + 32 <= hw) prefetch_l2((const float4*)p.rast + img + (size_t)gn * 32, 512);
+            }
+        }
         #pragma unroll
         for (int u = 0; u < IPF_UNROLL; u++)
         {
@@ -349,33 +358,13 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_fwd_fast(const InterpP
     }
 }
 
-// Round-2 experiment (off by default): IPG_FIXED=1 keeps the shared-memory copy of g_attr as 64-bit fixed point (2^-32
-// resolution), so that an add is one native shared-memory integer atomic instead of an fp32 compare-and-swap loop and the
-// per-CTA sums become order-independent; costs twice the shared memory.
-#ifndef IPG_FIXED
-#define IPG_FIXED 0
-#endif
-static __device__ __forceinline__ void acc_add(float* a, float v, bool smem)
-{
-#if IPG_FIXED
-    if (smem)
-    {
-        atomicAdd((unsigned long long*)a, (unsigned long long)__float2ll_rn(v * 4294967296.f));
-        return;
-    }
-#endif
-    (void)smem;
-    red_add(a, v);
-}
-
 template <int A, bool DA>
 __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const InterpParams p)
 {
     extern __shared__ __align__(16) float s_dyn[];
     constexpr int SK = (A == 3) ? (DA ? 6 : 3) : 1;
     float* s_stage = s_dyn;                                             // [8 warps][32 * SK]
-    float* s_acc = s_dyn + (IP_THREADS / 32) * 32 * SK;                 // [V * A] when use_smem_acc (IPG_FIXED: [V * A] 64-bit words)
-    constexpr int AW = IPG_FIXED ? 2 : 1;                               // floats per shared accumulator
+    float* s_acc = s_dyn + (IP_THREADS / 32) * 32 * SK;                 // [V * A] when use_smem_acc
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.y;
     const int hw = p.H * p.W;
@@ -392,7 +381,7 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const Interp
 
     if (p.use_smem_acc)
     {
-        for (int i = tid; i < acc_n * AW; i += IP_THREADS) s_acc[i] = 0.f;
+        for (int i = tid; i < acc_n; i += IP_THREADS) s_acc[i] = 0.f;
         __syncthreads();
     }
 
@@ -407,6 +396,16 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const Interp
             inb[u] = (g0 + u * wstride < groups) && (px < hw);
             r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (inb[u]) r[u] = ld_stream_f4((const float4*)p.rast + img + px);
+        }
+        if (lane == 0)                                  // this warp's next groups: ask L2 for their lines now
+        {
+            #pragma unroll
+            for (int u = 0; u < IPF_UNROLL; u++)
+            {
+                const int gn = g0 + (IPF_UNROLL + u) * wstride;
+                // only rast: dy / dda / rast_db are fetched under geometry only, prefetching them would add the bytes back
+                if (gn * 32 + 32 <= hw) prefetch_l2((const float4*)p.rast + img + (size_t)gn * 32, 512);
+            }
         }
         #pragma unroll
         for (int u = 0; u < IPF_UNROLL; u++)
@@ -440,11 +439,11 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const Interp
                 load_row<A>(p.attr + (size_t)vi2 * A, a2);
                 WarpRuns runs = warp_runs(valid ? float_to_triidx(r[u].w) : -1);
                 bool head = runs.is_head && valid;
-                const int aw = p.use_smem_acc ? AW : 1;
-                float* ga0 = acc + (size_t)(vi0 - voff) * A * aw;
-                float* ga1 = acc + (size_t)(vi1 - voff) * A * aw;
-                float* ga2 = acc + (size_t)(vi2 - voff) * A * aw;
+                float* ga0 = acc + (size_t)(vi0 - voff) * A;
+                float* ga1 = acc + (size_t)(vi1 - voff) * A;
+                float* ga2 = acc + (size_t)(vi2 - voff) * A;
                 float b0 = r[u].x, b1 = r[u].y, b2 = 1.f - r[u].x - r[u].y;
+                float t0[A], t1[A], t2[A];
                 #pragma unroll
                 for (int i = 0; i < A; i++)
                 {
@@ -452,17 +451,35 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const Interp
                     float dsdu = a0[i] - a2[i], dsdv = a1[i] - a2[i];
                     gr.x += y * dsdu;
                     gr.y += y * dsdv;
-                    float t0 = b0 * y, t1 = b1 * y, t2 = b2 * y;
+                    t0[i] = b0 * y; t1[i] = b1 * y; t2[i] = b2 * y;
                     if (DA)
                     {
                         float dsdx = valid ? dda[2 * i] : 0.f, dsdy = valid ? dda[2 * i + 1] : 0.f;
                         gdb.x += dsdu * dsdx; gdb.y += dsdu * dsdy; gdb.z += dsdv * dsdx; gdb.w += dsdv * dsdy;
                         float du = dsdx * db.x + dsdy * db.y;
                         float dv = dsdx * db.z + dsdy * db.w;
-                        t0 += du; t1 += dv; t2 += -du - dv;
+                        t0[i] += du; t1[i] += dv; t2[i] += -du - dv;
                     }
-                    t0 = warp_run_sum(t0, runs); t1 = warp_run_sum(t1, runs); t2 = warp_run_sum(t2, runs);
-                    if (head) { acc_add(ga0 + i * aw, t0, p.use_smem_acc); acc_add(ga1 + i * aw, t1, p.use_smem_acc); acc_add(ga2 + i * aw, t2, p.use_smem_acc); }
+                    t0[i] = warp_run_sum(t0[i], runs); t1[i] = warp_run_sum(t1[i], runs); t2[i] = warp_run_sum(t2[i], runs);
+                }
+                if (head)
+                {
+                    // global accumulation of 2- and 4-channel attributes: one vector reduction per vertex (REDG.F32x2 / x4);
+                    // the shared copy takes scalar adds (an fp32 add to shared memory is a compare-and-swap loop)
+                    if (!p.use_smem_acc && A == 2)
+                    {
+                        red_add2(ga0, make_float2(t0[0], t0[1 % A])); red_add2(ga1, make_float2(t1[0], t1[1 % A])); red_add2(ga2, make_float2(t2[0], t2[1 % A]));
+                    }
+                    else if (!p.use_smem_acc && A == 4)
+                    {
+                        red_add4(ga0, make_float4(t0[0], t0[1 % A], t0[2 % A], t0[3 % A])); red_add4(ga1, make_float4(t1[0], t1[1 % A], t1[2 % A], t1[3 % A]));
+                        red_add4(ga2, make_float4(t2[0], t2[1 % A], t2[2 % A], t2[3 % A]));
+                    }
+                    else
+                    {
+                        #pragma unroll
+                        for (int i = 0; i < A; i++) { red_add(ga0 + i, t0[i]); red_add(ga1 + i, t1[i]); red_add(ga2 + i, t2[i]); }
+                    }
                 }
                 if (!valid) { gr = make_float4(0.f, 0.f, 0.f, 0.f); gdb = gr; }
             }
@@ -479,11 +496,7 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const Interp
         __syncthreads();
         for (int i = tid; i < acc_n; i += IP_THREADS)
         {
-#if IPG_FIXED
-            float v = (float)((double)((const long long*)s_acc)[i] * (1.0 / 4294967296.0));
-#else
             float v = s_acc[i];
-#endif
             if (v != 0.f) red_add(gbase + i, v);
         }
     }
@@ -612,10 +625,10 @@ extern "C" int b200dr_interpolate_grad(const float* attr, const float* rast, con
     B200DR_CHECK(B200DR_ALIGNED16(g_rast) && B200DR_ALIGNED16(g_rast_db), "interpolate_grad(): gradient output tensors not aligned to float4");
     p.dy = dy; p.dda = dda; p.g_attr = g_attr; p.g_rast = g_rast; p.g_rast_db = g_rast_db;
 
-    if (fast_ok(p, da, attr) && B200DR_ALIGNED16(dy) && (!da || (((uintptr_t)dda) & 31) == 0))
+    if (fast_ok(p, da, attr) && B200DR_ALIGNED16(dy) && B200DR_ALIGNED16(g_attr) && (!da || (((uintptr_t)dda) & 31) == 0))
     {
         size_t stage_b = (size_t)(IP_THREADS / 32) * 32 * ((A == 3) ? (da ? 6 : 3) : 1) * sizeof(float);
-        size_t acc_b = (size_t)V * A * sizeof(float) * (IPG_FIXED ? 2 : 1);
+        size_t acc_b = (size_t)V * A * sizeof(float);
         p.use_smem_acc = (acc_b + stage_b <= 64 * 1024 && V <= ACC_SMEM_MAX_V) ? 1 : 0;
         size_t smem_f = stage_b + (p.use_smem_acc ? acc_b : 0);
         int groups = (int)(((size_t)H * W + 31) / 32);

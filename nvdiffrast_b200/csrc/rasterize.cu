@@ -38,6 +38,8 @@ struct RastParams
     // BINS scratch
     int*            extra;          // [N] extra (clipped) sub-triangle counters
     uint2*          bbox;           // [N, cap]
+    uint2*          cbox;           // [N, nchunk]: union of the bounding boxes of 32 consecutive triangle slots ("chunk")
+    int             nchunk;         // chunk boxes per image (even, so that every image's array is a 16-byte aligned TMA source)
     uint4*          rec;            // [N, cap, 2]
     // SCATTER scratch
     unsigned long long* keys;       // [N,H,W]
@@ -285,6 +287,7 @@ static __device__ __forceinline__ Edge make_edge(int ax, int ay, int bx, int by,
 #define BIN_LIST   256          // triangles set up in shared memory at a time (longer per-bin lists are processed in chunks)
 #define BIN_IDX    2048         // records scanned per segment = capacity of the per-bin index list
 #define BIN_THREADS 256
+#define BIN_MAXCHUNK 1024       // chunk boxes per image that fit the staging area: the BINS path takes at most 32768 triangles per image
 
 struct __align__(16) BinTri     // 64 bytes, broadcast-read by every thread of the CTA
 {
@@ -296,14 +299,16 @@ struct __align__(16) BinTri     // 64 bytes, broadcast-read by every thread of t
 
 struct SetupEmitRecords
 {
-    const RastParams& p; int n; int slot0; int emitted; int id;
+    const RastParams& p; int n; int slot0; int emitted; int id; uint2 first;    // first: bounding box that went to slot0
     __device__ __forceinline__ void operator()(const SubTri& s)
     {
         int slot = slot0;
         if (emitted > 0) slot = p.max_tris + atomicAdd(p.extra + n, 1);
-        emitted++;
         size_t base = (size_t)n * p.cap + slot;
-        p.bbox[base] = make_uint2((uint32_t)s.bx0 | ((uint32_t)s.bx1 << 16), (uint32_t)s.by0 | ((uint32_t)s.by1 << 16));
+        const uint2 box = make_uint2((uint32_t)s.bx0 | ((uint32_t)s.bx1 << 16), (uint32_t)s.by0 | ((uint32_t)s.by1 << 16));
+        if (emitted == 0) first = box;
+        emitted++;
+        p.bbox[base] = box;
         p.rec[base * 2 + 0] = make_uint4(((uint32_t)s.x0 & 0xFFFFu) | ((uint32_t)s.y0 << 16), ((uint32_t)s.x1 & 0xFFFFu) | ((uint32_t)s.y1 << 16),
                                           ((uint32_t)s.x2 & 0xFFFFu) | ((uint32_t)s.y2 << 16), s.zx);
         p.rec[base * 2 + 1] = make_uint4(s.zy, s.zb, (uint32_t)id, 0u);
@@ -345,25 +350,41 @@ static __device__ __forceinline__ void image_range(const RastParams& p, int n, i
     else { start = __ldg(p.ranges + 2 * n); count = __ldg(p.ranges + 2 * n + 1); }
 }
 
+// Thread per (image, triangle).  Besides the records, every warp writes the union of its 32 first-slot bounding boxes: meshes
+// keep neighbouring triangles at neighbouring indices, so a bin can discard 32 triangles with one test (raster_bins_kernel).
 __global__ void __launch_bounds__(128) raster_setup_kernel(const RastParams p)
 {
     int t = blockIdx.x * 128 + threadIdx.x;
     int n = blockIdx.y;
-    if (t >= p.max_tris) return;
     int start, count;
     image_range(p, n, start, count);
-    SetupEmitRecords emit = { p, n, t, 0, 0 };
-    if (t < count)
+    SetupEmitRecords emit = { p, n, t, 0, 0, make_uint2(0x0000FFFFu, 0x0000FFFFu) };                    // empty box: lo > hi
+    uint2 bb = emit.first;
+    if (t < p.max_tris)
     {
-        int triIdx = start + t;
-        if ((uint32_t)triIdx < (uint32_t)p.T)
+        if (t < count)
         {
-            emit.id = triIdx + 1;
-            process_triangle(p, n, triIdx, emit);
+            int triIdx = start + t;
+            if ((uint32_t)triIdx < (uint32_t)p.T)
+            {
+                emit.id = triIdx + 1;
+                process_triangle(p, n, triIdx, emit);
+            }
         }
+        if (emit.emitted == 0) p.bbox[(size_t)n * p.cap + t] = bb;
+        else                   bb = emit.first;
     }
-    if (emit.emitted == 0)
-        p.bbox[(size_t)n * p.cap + t] = make_uint2(0x0000FFFFu, 0x0000FFFFu);   // empty: lo > hi
+    // union over the warp (whole warps stay alive for the shuffles; lanes without a box contribute the empty box)
+    int x0 = (int)(bb.x & 0xFFFFu), x1 = (int)(bb.x >> 16), y0 = (int)(bb.y & 0xFFFFu), y1 = (int)(bb.y >> 16);
+    if (x0 > x1) { x0 = 0xFFFF; x1 = 0; y0 = 0xFFFF; y1 = 0; }
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, d)); x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, d));
+        y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, d)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, d));
+    }
+    if ((threadIdx.x & 31) == 0 && (t >> 5) < p.nchunk)
+        p.cbox[(size_t)n * p.nchunk + (t >> 5)] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
 }
 
 static __device__ __forceinline__ int s16lo(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
@@ -374,10 +395,12 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
 {
     __shared__ BinTri   s_tri[BIN_LIST];            // 16 KB
     __shared__ int      s_idx[BIN_IDX];             //  8 KB
-    __shared__ __align__(16) uint32_t s_ids[BIN_SIZE * BIN_SIZE]; // 16 KB; during the scan: staging buffer of one bbox segment
+    __shared__ __align__(16) uint32_t s_ids[BIN_SIZE * BIN_SIZE]; // 16 KB; during the scan: chunk boxes + hit chunks + per-warp lists
     __shared__ __align__(8) unsigned long long s_mbar;
-    __shared__ int      s_count;
-    uint2* const s_bb = (uint2*)s_ids;              // BIN_IDX bounding boxes = 16 KB, filled by a TMA bulk copy per segment
+    __shared__ int      s_count, s_nhit;
+    uint2* const s_cb = (uint2*)s_ids;                                  // [BIN_MAXCHUNK] chunk boxes of this image (8 KB), one TMA bulk copy
+    unsigned short* const s_hit = (unsigned short*)(s_ids + 2 * BIN_MAXCHUNK);            // [BIN_IDX / 32] chunks of the segment that touch the bin
+    unsigned char* const s_wl = (unsigned char*)(s_ids + 2 * BIN_MAXCHUNK + BIN_IDX / 64); // [8 warps][BIN_LIST] per-warp triangle lists
 
     const int tid = threadIdx.x;
     const int n = blockIdx.z;
@@ -386,8 +409,11 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
 
     // Thread -> 4x4 pixel block.  A warp covers 32x16 pixels (8x4 blocks).
     const int lane = tid & 31, warp = tid >> 5;
-    const int tx = ((warp & 1) << 5) + ((lane & 7) << 2);
-    const int ty = ((warp >> 1) << 4) + ((lane >> 3) << 2);
+    const int wx = (warp & 1) << 5, wy = (warp >> 1) << 4;             // this warp's 32x16 region, bin-relative
+    const int tx = wx + ((lane & 7) << 2);
+    const int ty = wy + ((lane >> 3) << 2);
+
+    if (tid == 0) mbar_init(&s_mbar, 1);
 
     uint32_t bestD[16], bestI[16], peelD[16];
     #pragma unroll
@@ -416,35 +442,66 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
     const int total = p.max_tris + min(p.extra[n], p.cap - p.max_tris);
     const uint2* bboxes = p.bbox + (size_t)n * p.cap;
     const uint4* recs = p.rec + (size_t)n * p.cap * 2;
+    const unsigned lt = (1u << lane) - 1u;
 
     bool any = false;
-    // Records are scanned in segments of BIN_IDX records (the index list cannot overflow); within a segment the scan loop
-    // has no barrier: every thread tests bounding boxes and appends the indices of this bin's triangles to s_idx.
-    if (tid == 0) mbar_init(&s_mbar, 1);
     uint32_t phase = 0;
+    __syncthreads();                                            // barrier initialised
+    // Records are scanned in segments of BIN_IDX records (the index list cannot overflow).  Two levels: a thread tests the
+    // union box of a chunk of 32 consecutive slots (staged above); warps then expand the chunks that touch the bin, one
+    // coalesced 256-byte read of the 32 boxes each, and append the hits to s_idx with one shared-memory atomic per chunk.
+    // Clipped extras (slots >= max_tris, rare) have no chunk boxes and are tested one by one.
     for (int seg = 0; seg < total; seg += BIN_IDX)
     {
         const int seg_end = min(seg + BIN_IDX, total);
+        const int c0 = seg >> 5, cb_base = c0 & ~(BIN_MAXCHUNK - 1);
         if (tid == 0)
         {
-            s_count = 0;
-            // one TMA bulk copy brings the segment's bounding boxes into shared memory (cap is even, so the source is
-            // 16-byte aligned; an odd count is rounded up and reads one slot of the same array that is then ignored)
-            tma_load_1d(s_bb, bboxes + seg, (uint32_t)(((seg_end - seg) * 8 + 15) & ~15), &s_mbar);
+            s_count = 0; s_nhit = 0;
+            // every BIN_MAXCHUNK chunks (= 32768 triangles; once per image for any scene the BINS path is picked for) the next
+            // slab of chunk boxes is staged into shared memory by one TMA bulk copy; nchunk is even: a multiple of 16 bytes
+            if (c0 == cb_base && c0 < p.nchunk)
+                tma_load_1d(s_cb, p.cbox + (size_t)n * p.nchunk + c0, (uint32_t)min(BIN_MAXCHUNK, p.nchunk - c0) * 8u, &s_mbar);
         }
         __syncthreads();
-        mbar_wait(&s_mbar, phase);
-        phase ^= 1u;
-        for (int i = seg + tid; i < seg_end; i += BIN_THREADS)
+        if (c0 == cb_base && c0 < p.nchunk) { mbar_wait(&s_mbar, phase); phase ^= 1u; }
+        const int c_end = (min(seg_end, p.max_tris) + 31) >> 5;
+        for (int c = c0 + tid; c < c_end; c += BIN_THREADS)
         {
-            uint2 bb = s_bb[i - seg];
+            uint2 cb = s_cb[c - cb_base];
+            int x0 = (int)(cb.x & 0xFFFFu), x1 = (int)(cb.x >> 16), y0 = (int)(cb.y & 0xFFFFu), y1 = (int)(cb.y >> 16);
+            if (x0 <= binX1 && x1 >= binX0 && y0 <= binY1 && y1 >= binY0) s_hit[atomicAdd(&s_nhit, 1)] = (unsigned short)(c - c0);
+        }
+        for (int i = max(seg, p.max_tris) + tid; i < seg_end; i += BIN_THREADS)
+        {
+            uint2 bb = __ldg(bboxes + i);
             int x0 = (int)(bb.x & 0xFFFFu), x1 = (int)(bb.x >> 16), y0 = (int)(bb.y & 0xFFFFu), y1 = (int)(bb.y >> 16);
-            if (x0 <= binX1 && x1 >= binX0 && y0 <= binY1 && y1 >= binY0 && x0 <= x1)
-                s_idx[atomicAdd(&s_count, 1)] = i;
+            if (x0 <= binX1 && x1 >= binX0 && y0 <= binY1 && y1 >= binY0 && x0 <= x1) s_idx[atomicAdd(&s_count, 1)] = i;
+        }
+        __syncthreads();
+        const int nhit = s_nhit;
+        for (int h = warp; h < nhit; h += BIN_THREADS / 32)
+        {
+            const int i = ((c0 + (int)s_hit[h]) << 5) + lane;
+            bool hit = false;
+            if (i < p.max_tris)
+            {
+                uint2 bb = __ldg(bboxes + i);
+                int x0 = (int)(bb.x & 0xFFFFu), x1 = (int)(bb.x >> 16), y0 = (int)(bb.y & 0xFFFFu), y1 = (int)(bb.y >> 16);
+                hit = x0 <= binX1 && x1 >= binX0 && y0 <= binY1 && y1 >= binY0 && x0 <= x1;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m)
+            {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_count, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (hit) s_idx[base + __popc(m & lt)] = i;
+            }
         }
         __syncthreads();
         const int nidx = s_count;
-        __syncthreads();                                        // every thread has read the count before the next segment resets it
+        __syncthreads();                                        // every thread has read the counts before the next segment resets them
         if (nidx > 0) any = true;
 
         // ---- rasterize this bin's triangles, BIN_LIST at a time
@@ -454,7 +511,7 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
             for (int j = tid; j < cnt; j += BIN_THREADS)        // bin-relative edge / depth setup, one triangle per thread
             {
                 int i = s_idx[lb + j];
-                uint2 bb = s_bb[i - seg];
+                uint2 bb = __ldg(bboxes + i);
                 int x0 = (int)(bb.x & 0xFFFFu), x1 = (int)(bb.x >> 16), y0 = (int)(bb.y & 0xFFFFu), y1 = (int)(bb.y >> 16);
                 uint4 ra = __ldg(recs + i * 2), rb = __ldg(recs + i * 2 + 1);
                 int ax = s16lo(ra.x), ay = s16hi(ra.x), bx = s16lo(ra.y), by = s16hi(ra.y), cx = s16lo(ra.z), cy = s16hi(ra.z);
@@ -474,8 +531,28 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
                 s_tri[j] = t;
             }
             __syncthreads();
-            for (int k = 0; k < cnt; k++)
+            // per-warp list: the triangles of this batch whose (bin-clipped) box touches the warp's 32x16 pixels.  Every lane then
+            // walks a list ~4-8x shorter than the bin's, with warp-uniform trip count.
+            unsigned char* wl = s_wl + warp * BIN_LIST;
+            int wn = 0;
+            for (int j0 = 0; j0 < cnt; j0 += 32)
             {
+                const int k = j0 + lane;
+                bool hit = false;
+                if (k < cnt)
+                {
+                    uint32_t box = s_tri[k].box;
+                    int x0 = (int)(box & 0xFF), x1 = (int)((box >> 8) & 0xFF), y0 = (int)((box >> 16) & 0xFF), y1 = (int)(box >> 24);
+                    hit = !(wx > x1 || wx + 31 < x0 || wy > y1 || wy + 15 < y0);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (hit) wl[wn + __popc(m & lt)] = (unsigned char)k;
+                wn += __popc(m);
+            }
+            __syncwarp();
+            for (int q_ = 0; q_ < wn; q_++)
+            {
+                const int k = wl[q_];
                 uint32_t box = s_tri[k].box;
                 int x0 = (int)(box & 0xFF), x1 = (int)((box >> 8) & 0xFF), y0 = (int)((box >> 16) & 0xFF), y1 = (int)(box >> 24);
                 if (tx > x1 || tx + 3 < x0 || ty > y1 || ty + 3 < y0) continue;
@@ -757,9 +834,6 @@ static __device__ __forceinline__ void raster_grad_pixel(const RastGradParams& p
 #ifndef ACC_SMEM_MAX_V
 #define ACC_SMEM_MAX_V (1 << 30)
 #endif
-#ifndef RG_COND_LOADS
-#define RG_COND_LOADS 0
-#endif
 #ifndef RG_UNROLL
 #define RG_UNROLL 2
 #endif
@@ -795,18 +869,19 @@ __global__ void __launch_bounds__(256, RG_MINB) raster_grad_kernel(const RastGra
             int r = (g0 + u * wstride) * 32 + lane;
             inb[u] = (g0 + u * wstride < groups) && (r < hw);
             ro[u] = make_float4(0.f, 0.f, 0.f, 0.f); ddb[u] = ro[u]; dy[u] = make_float2(0.f, 0.f);
-            if (inb[u])
+            if (inb[u]) ro[u] = ld_stream_f4((const float4*)p.rast + img + r);
+        }
+        if (lane == 0)                                  // this warp's next groups: ask L2 for their rast lines now
+        {
+            #pragma unroll
+            for (int u = 0; u < RG_UNROLL; u++)
             {
-                ro[u] = ld_stream_f4((const float4*)p.rast + img + r);
-#if !RG_COND_LOADS
-                dy[u] = ld_stream_f2((const float2*)p.dy + (img + r) * 2);
-                if (ENABLE_DB) ddb[u] = ld_stream_f4((const float4*)p.ddb + img + r);
-#endif
+                const int gn = g0 + (RG_UNROLL + u) * wstride;
+                if (gn * 32 + 32 <= hw) prefetch_l2((const float4*)p.rast + img + (size_t)gn * 32, 512);
             }
         }
-#if RG_COND_LOADS
-        // round-2 experiment (off by default): incoming gradients are fetched only under geometry (empty pixels then cost
-        // 16 instead of 40-48 bytes); the extra dependency runs in parallel with the triangle -> vertex gathers
+        // incoming gradients are fetched only under geometry (empty pixels cost 16 instead of 40-48 bytes); the extra
+        // dependency runs in parallel with the triangle -> vertex gathers
         #pragma unroll
         for (int u = 0; u < RG_UNROLL; u++)
         {
@@ -817,7 +892,6 @@ __global__ void __launch_bounds__(256, RG_MINB) raster_grad_kernel(const RastGra
                 if (ENABLE_DB) ddb[u] = ld_stream_f4((const float4*)p.ddb + img + r);
             }
         }
-#endif
         #pragma unroll
         for (int u = 0; u < RG_UNROLL; u++)
         {
@@ -851,9 +925,18 @@ __global__ void __launch_bounds__(256, RG_MINB) raster_grad_kernel(const RastGra
             for (int i = 0; i < 9; i++) gv[i] = warp_run_sum(gv[i], runs);
             if (runs.is_head && triIdx >= 0)
             {
-                red_add(acc + 4 * vi0 + 0, gv[0]); red_add(acc + 4 * vi0 + 1, gv[1]); red_add(acc + 4 * vi0 + 3, gv[2]);
-                red_add(acc + 4 * vi1 + 0, gv[3]); red_add(acc + 4 * vi1 + 1, gv[4]); red_add(acc + 4 * vi1 + 3, gv[5]);
-                red_add(acc + 4 * vi2 + 0, gv[6]); red_add(acc + 4 * vi2 + 1, gv[7]); red_add(acc + 4 * vi2 + 3, gv[8]);
+                if (p.use_smem)     // shared copy: an fp32 add is a compare-and-swap loop (ATOMS.CAST.SPIN), one per component
+                {
+                    red_add(acc + 4 * vi0 + 0, gv[0]); red_add(acc + 4 * vi0 + 1, gv[1]); red_add(acc + 4 * vi0 + 3, gv[2]);
+                    red_add(acc + 4 * vi1 + 0, gv[3]); red_add(acc + 4 * vi1 + 1, gv[4]); red_add(acc + 4 * vi1 + 3, gv[5]);
+                    red_add(acc + 4 * vi2 + 0, gv[6]); red_add(acc + 4 * vi2 + 1, gv[7]); red_add(acc + 4 * vi2 + 3, gv[8]);
+                }
+                else                // global: one 128-bit vector reduction per vertex (z receives +0)
+                {
+                    red_add4(acc + 4 * vi0, make_float4(gv[0], gv[1], 0.f, gv[2]));
+                    red_add4(acc + 4 * vi1, make_float4(gv[3], gv[4], 0.f, gv[5]));
+                    red_add4(acc + 4 * vi2, make_float4(gv[6], gv[7], 0.f, gv[8]));
+                }
             }
         }
     }
@@ -890,8 +973,10 @@ extern "C" size_t b200dr_rasterize_scratch_bytes(int N, int max_tris, int H, int
     if (path == B200DR_RAST_AUTO) path = b200dr_rasterize_pick_path(N, max_tris, H, W);
     if (path == B200DR_RAST_BINS)
     {
-        size_t cap = ((size_t)7 * max_tris + 1) & ~(size_t)1;   // even: every image's bbox array stays 16-byte aligned (TMA bulk copies)
-        return align_up((size_t)N * sizeof(int), 256) + align_up((size_t)N * cap * sizeof(uint2), 256) + (size_t)N * cap * 2 * sizeof(uint4);
+        size_t cap = ((size_t)7 * max_tris + 1) & ~(size_t)1;
+        size_t nchunk = ((((size_t)max_tris + 31) >> 5) + 1) & ~(size_t)1;   // even: every image's chunk-box array stays a 16-byte aligned TMA source
+        return align_up((size_t)N * sizeof(int), 256) + align_up((size_t)N * nchunk * sizeof(uint2), 256) +
+               align_up((size_t)N * cap * sizeof(uint2), 256) + (size_t)N * cap * 2 * sizeof(uint4);
     }
     return (size_t)N * H * W * sizeof(unsigned long long);
 }
@@ -930,7 +1015,9 @@ extern "C" int b200dr_rasterize_fwd(const float* pos, const int32_t* tri, const 
     if (path == B200DR_RAST_BINS)
     {
         char* s = (char*)scratch;
+        p.nchunk = (((max_tris + 31) >> 5) + 1) & ~1;
         p.extra = (int*)s;                    s += align_up((size_t)N * sizeof(int), 256);
+        p.cbox = (uint2*)s;                   s += align_up((size_t)N * p.nchunk * sizeof(uint2), 256);
         p.bbox = (uint2*)s;                   s += align_up((size_t)N * p.cap * sizeof(uint2), 256);
         p.rec = (uint4*)s;
     }

@@ -28,8 +28,21 @@ def _worker(rank, world, port, q):
     g_attr = torch.from_numpy(g["attr"].copy())                  # shared parameter: vertex colours
     g_pos_sum = torch.from_numpy(g["pos"].sum(0).copy())         # stand-in for a shared-mesh gradient
     allreduce_shared_grads([g_attr, g_pos_sum])
+    # bucketed reducer (the path bench.py uses): hooks on the leaves, the large slot goes out early (async), the small tail in
+    # one call at finish(); a parameter that received no gradient this step contributes zeros
+    from nvdiffrast_b200.distributed import SharedGradReducer
+    big = torch.arange(40, dtype=torch.float32).reshape(2, 20).requires_grad_(True)
+    small = torch.ones(3, 4).requires_grad_(True)
+    unused = torch.ones(5).requires_grad_(True)
+    red = SharedGradReducer([("small", small.shape), ("big", big.shape), ("unused", unused.shape)], "cpu", early_bytes=64)
+    assert red.early == {"big"} and red.bytes_per_step == (40 + 12 + 5) * 4
+    for step in range(2):                                        # reused across steps
+        red.begin({"big": big, "small": small, "unused": unused})
+        big.grad = None; small.grad = None
+        ((big * (rank + 1 + step)).sum() + (small * small * (rank + 2)).sum()).backward()
+        out = red.finish()
     if rank == 0:
-        q.put((g_attr.numpy(), g_pos_sum.numpy()))
+        q.put((g_attr.numpy(), g_pos_sum.numpy(), {k: v.clone().numpy() for k, v in out.items()}))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -47,7 +60,7 @@ def test_sharded_gradients_match_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got_attr, got_pos = q.get(timeout=300)
+    got_attr, got_pos, red = q.get(timeout=300)
     for p in procs:
         p.join(timeout=300)
         assert p.exitcode == 0
@@ -57,3 +70,7 @@ def test_sharded_gradients_match_single_process():
     _, _, _, g = oracle_chain(c, n_total, False, dy)
     assert np.allclose(got_attr, g["attr"], rtol=1e-5, atol=1e-5)
     assert np.allclose(got_pos, g["pos"].sum(0), rtol=1e-4, atol=1e-4)
+    # reducer, second step (step = 1): d/d big = (rank + 2) summed over ranks 0, 1 = 5; d/d small = 2 (rank + 2) summed = 10; unused = 0
+    assert np.array_equal(red["big"], np.full((2, 20), 5.0, np.float32))
+    assert np.array_equal(red["small"], np.full((3, 4), 10.0, np.float32))
+    assert np.array_equal(red["unused"], np.zeros(5, np.float32))

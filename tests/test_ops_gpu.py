@@ -327,6 +327,25 @@ def test_texture_uniform_regions(dr, filter_mode, boundary_mode, texD):
     _texture_case_vs_oracle(dr, tex, uv, uv_da if mip else None, None, filter_mode, boundary_mode, dy, "uniform")
 
 
+@pytest.mark.parametrize("filter_mode", ["linear", "linear-mipmap-linear"])
+def test_texture_zero_boundary_pixel_aligned_rows(dr, filter_mode):
+    """Texel-aligned sampling in the half-texel band outside a zero-padded texture: u steps exactly one texel per pixel and
+    v sits above row 0, so every lane of a warp has the same bilinear weights and the same (missing, -1) first tap while the
+    remaining taps differ from lane to lane.  A uniform-group test that looks at the first tap and two weights only would
+    sum the whole warp into one lane's texels (round-1 advisor finding); also covers the mirrored pair (u,v) / (1-v,1-u)."""
+    N, H, W, C = 1, 8, 64, 3
+    rng = np.random.default_rng(35)
+    tex = rng.uniform(size=(1, 32, 32, C)).astype(np.float32)
+    xs = np.arange(W, dtype=np.float32)
+    uv = np.zeros((N, H, W, 2), np.float32)
+    uv[..., 0] = ((xs % 30) + 0.75) / 32.0                    # u*w - 0.5 = x + 0.25: integer part differs per lane, fraction identical
+    uv[:, :4, :, 1] = 0.25 / 32.0                             # v*h - 0.5 = -0.25: upper taps outside (zero mode -> index -1)
+    uv[:, 4:, :, 1] = 31.75 / 32.0                            # lower taps outside
+    uv[0, 2, 1::2] = np.stack([1.0 - uv[0, 2, 1::2, 1], 1.0 - uv[0, 2, 1::2, 0]], -1)                                # mirrored partners
+    uv_da = np.zeros((N, H, W, 4), np.float32) if "mipmap" in filter_mode else None
+    _texture_case_vs_oracle(dr, tex, uv, uv_da, None, filter_mode, "zero", _rand_like((N, H, W, C), 36), "zero aligned")
+
+
 def test_texture_mip_stack_and_wrapper(dr):
     rng = np.random.default_rng(18)
     tex = rng.uniform(size=(1, 16, 32, 3)).astype(np.float32)
