@@ -167,6 +167,25 @@ int b200dr_texture_grad(const float* tex, const float* const* mip_ptrs, int max_
                         float* g_uv, float* g_uv_da, float* g_bias,
                         void* scratch, size_t scratch_bytes, void* stream);
 
+/* EXTENSION (no counterpart in the reference's binding; SURVEY.md 8(f)-4 "kernel fusion behind the same API"): the backward of
+ * texture(interpolate(attr, rasterize(pos))) in ONE pass.  Equivalent to texture_grad_* followed by interpolate_grad_da
+ * (torch_interpolate.cpp:137-248) and, when pos != NULL, rasterize_grad_db (torch_rasterize.cpp:171-262), without the g_uv /
+ * g_uv_da / g_rast / g_rast_db round trips through memory: uv and uv_da are recomputed from attr [Va,2] (or [N,Va,2] with
+ * attr_per_image) through attr_tri, rast and rast_db.  Preconditions the caller guarantees: 2-D texture modes, C <= 4, no
+ * mip_level_bias, internal mip stack; uv (and uv_da) of the forward call were exactly interpolate's outputs on these inputs
+ * with diff_attrs = all.  Outputs (each may be NULL when that gradient is not needed): g_tex (unpadded, fully written),
+ * g_attr (zero-initialised by the caller, accumulated), g_pos [N,V,4] (zero-initialised, accumulated; instanced mode only),
+ * or -- pos == NULL -- g_rast / g_rast_db [N,H,W,4] (fully written).  grad_db: rasterize() was called with grad_db=True.
+ * rast_db may be NULL for filter_mode linear.  scratch as in b200dr_texture_grad. */
+int b200dr_texture_chain_grad(const float* tex, const float* const* mip_ptrs, int max_level, const float* dy,
+                              const float* attr, const int32_t* attr_tri, int Va, int attr_per_image,
+                              const float* rast, const float* rast_db,
+                              const float* pos, const int32_t* pos_tri, int V, int grad_db,
+                              int N, int H, int W, int T, int texD, int texH, int texW, int C,
+                              int filter_mode, int boundary_mode,
+                              float* g_tex, float* g_attr, float* g_rast, float* g_rast_db, float* g_pos,
+                              void* scratch, size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

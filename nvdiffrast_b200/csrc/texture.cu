@@ -13,6 +13,7 @@
 // (REDG.E.ADD.F32x4: one atomic per texel instead of one per texel channel), then a resolve pass pulls the mip levels
 // down to the base level and writes the gradient in the caller's channel layout.
 #include "common.cuh"
+#include "pixel_math.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -807,10 +808,15 @@ static __device__ __forceinline__ float dot4(float4 k, const float (&dy)[C])
     return r;
 }
 
-template <int C, int B>
-static __device__ __forceinline__ void texgrad_group(const TexParams& p, const TexMode& m, const TexGradIn<C>& in, Pending<C>& pd, bool& cached,
-                                                     UniGradSlot* slot, int lane, float* sw, size_t hw, bool trilinear)
+// Per-pixel results of one group: gradient w.r.t. uv, the level (bias) and uv_da.  The stand-alone texture backward stores them
+// (STORE); the fused chain backward keeps them in registers and feeds them straight into the interpolate / rasterize math.
+struct TexPixelGrad { float gu, gv, df; float4 gda; };
+
+template <int C, int B, bool STORE>
+static __device__ __forceinline__ TexPixelGrad texgrad_group(const TexParams& p, const TexMode& m, const TexGradIn<C>& in, Pending<C>& pd, bool& cached,
+                                                             UniGradSlot* slot, int lane, float* sw, size_t hw, bool trilinear)
 {
+    TexPixelGrad res; res.gu = 0.f; res.gv = 0.f; res.df = 0.f; res.gda = make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t pidx = in.pidx;
     const bool inb = in.inb;
     float dy[C];
@@ -829,10 +835,14 @@ static __device__ __forceinline__ void texgrad_group(const TexParams& p, const T
         TEX_COUNT(3);
         #pragma unroll
         for (int i = 0; i < C; i++) pd.sum[i] += dy[i];
-        if (p.g_uv) st_stream_f2((float2*)p.g_uv + pidx, make_float2(dot4<C>(slot->ku, dy), dot4<C>(slot->kv, dy)));
-        if (p.g_bias) st_stream_f(p.g_bias + pidx, 0.f);
-        if (p.g_uv_da) st_stream_f4((float4*)p.g_uv_da + pidx, make_float4(0.f, 0.f, 0.f, 0.f));
-        return;
+        res.gu = dot4<C>(slot->ku, dy); res.gv = dot4<C>(slot->kv, dy);
+        if (STORE)
+        {
+            if (p.g_uv) st_stream_f2((float2*)p.g_uv + pidx, make_float2(res.gu, res.gv));
+            if (p.g_bias) st_stream_f(p.g_bias + pidx, 0.f);
+            if (p.g_uv_da) st_stream_f4((float4*)p.g_uv_da + pidx, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        return res;
     }
 
     TEX_COUNT(4);
@@ -982,12 +992,14 @@ static __device__ __forceinline__ void texgrad_group(const TexParams& p, const T
             }
         }
     }
-    if (inb)
+    res.gu = gu; res.gv = gv; res.df = df; res.gda = make_float4(dw.x * df, dw.y * df, dw.z * df, dw.w * df);
+    if (STORE && inb)
     {
         if (p.g_uv) st_stream_f2((float2*)p.g_uv + pidx, make_float2(gu, gv));
         if (p.g_bias) st_stream_f(p.g_bias + pidx, df);
-        if (p.g_uv_da) st_stream_f4((float4*)p.g_uv_da + pidx, make_float4(dw.x * df, dw.y * df, dw.z * df, dw.w * df));
+        if (p.g_uv_da) st_stream_f4((float4*)p.g_uv_da + pidx, res.gda);
     }
+    return res;
 }
 
 template <int C, int F, int B>
@@ -1030,7 +1042,216 @@ __global__ void __launch_bounds__(TEXG_THREADS, TEXG_MINB) texture_grad_fast(con
         }
         #pragma unroll
         for (int u = 0; u < TEXG_UNROLL; u++)
-            if (in[u].g < groups) texgrad_group<C, B>(p, m, in[u], pd, cached, &s_slot[warp], lane, s_stage[warp], hw, trilinear);      // warp-uniform
+            if (in[u].g < groups) texgrad_group<C, B, true>(p, m, in[u], pd, cached, &s_slot[warp], lane, s_stage[warp], hw, trilinear);   // warp-uniform
+    }
+    pending_flush<C>(pd, p, lane);
+}
+
+// ================================================================================================
+// Fused chain backward: texture backward -> interpolate backward -> rasterize backward in one pass.
+//
+// The op boundaries of the reference API force a tensor round trip between consecutive backward ops: texture_grad writes
+// g_uv / g_uv_da (24 B/px) which interpolate_grad reads back together with rast, rast_db, and writes g_rast / g_rast_db
+// (32 B/px) which rasterize_grad reads back with rast again.  When the front end can prove that texture()'s uv / uv_da are
+// the untouched outputs of interpolate(attr, rast, rast_db, diff_attrs='all') on the untouched outputs of rasterize(pos),
+// it routes the texture gradient through this kernel instead: per pixel it reads rast, rast_db and dy only (44 B instead of
+// 196), RECOMPUTES uv / uv_da from the vertex attributes (same expressions as interpolate_fwd_fast), and keeps the chain
+//      dy -> (g_uv, g_uv_da) -> (g_attr; g_rast, g_rast_db) -> g_pos
+// in registers.  Background pixels (no triangle) cost rast + dy and a register add (their texel gradient joins the pending
+// sums of the quad at uv = 0).  RASTER = false stops after interpolate backward and writes g_rast / g_rast_db (range-mode
+// meshes, or rast consumers the front end cannot see through).
+// ================================================================================================
+
+struct ChainParams
+{
+    const float* rast; const float* rast_db;            // [N,H,W,4]
+    const float* attr; const int32_t* attr_tri;         // [Va,2] (shared by all images) or [N,Va,2]; [T,3]
+    const float* pos; const int32_t* pos_tri;           // RASTER: [N,V,4]; [T,3]
+    float* g_attr; float* g_pos;                        // nullable: gradient not required
+    float* g_rast; float* g_rast_db;                    // !RASTER
+    int Va, V, T, attr_per_image, grad_db;
+    float xs, xo, ys, yo;
+};
+
+// uv = b0 a0 + b1 a1 + b2 a2 and its screen-space derivatives: the expressions of interpolate_fwd_fast (A = 2, all
+// differentials), kept textually identical so that the recomputed values are the ones the forward pass stored.
+static __device__ __forceinline__ void interp_uv(float4 r, float4 db, const float (&a0)[2], const float (&a1)[2], const float (&a2)[2], float2& uv, float4& da)
+{
+    float b0 = r.x, b1 = r.y, b2 = 1.f - r.x - r.y;
+    float o[2], oda[4];
+    #pragma unroll
+    for (int i = 0; i < 2; i++)
+    {
+        o[i] = b0 * a0[i] + b1 * a1[i] + b2 * a2[i];
+        float dsdu = a0[i] - a2[i], dsdv = a1[i] - a2[i];
+        oda[2 * i] = db.x * dsdu + db.z * dsdv;
+        oda[2 * i + 1] = db.y * dsdu + db.w * dsdv;
+    }
+    uv = make_float2(o[0], o[1]);
+    da = make_float4(oda[0], oda[1], oda[2], oda[3]);
+}
+
+#ifndef TCG_MINB
+#define TCG_MINB 4
+#endif
+
+template <int C, int F, int B, bool RASTER>
+__global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fast(const TexParams p, const ChainParams q)
+{
+    const TexMode m = tex_mode_static<F, B>(p);
+    constexpr int SK = (C == 3) ? 3 : 1;
+    __shared__ __align__(16) float s_stage[TEXG_THREADS / 32][32 * SK];
+    __shared__ __align__(16) UniGradSlot s_slot[TEXG_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t hw = (size_t)p.H * p.W;
+    const size_t total = hw * p.N;
+    const size_t groups = (total + 31) >> 5;
+    const size_t wstride = (size_t)gridDim.x * (TEXG_THREADS / 32);
+    const bool trilinear = (m.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
+    Pending<C> pd;
+    pd.level = -1; pd.tc = make_int4(-1, -1, -1, -1); pd.fu = 0.f; pd.fv = 0.f; pd.w = make_float4(0.f, 0.f, 0.f, 0.f);
+    #pragma unroll
+    for (int i = 0; i < C; i++) pd.sum[i] = 0.f;
+    bool cached = false;
+
+    for (size_t g = (size_t)blockIdx.x * (TEXG_THREADS / 32) + warp; g < groups; g += wstride)
+    {
+        TexGradIn<C> in;
+        in.g = g; in.pidx = g * 32 + lane;
+        in.inb = in.pidx < total; in.full = (g * 32 + 32 <= total);
+        in.bias = 0.f;
+        const size_t pidx = in.pidx;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in.inb) r = ld_stream_f4((const float4*)q.rast + pidx);
+        warp_load_aos_issue<C>(p.dy + g * 32 * C, in.dy, lane, in.inb, in.full);
+        if (lane == 0)                                  // this warp's next group: ask L2 for its rast and dy lines now
+        {
+            const size_t gn = g + wstride;
+            if (gn * 32 + 32 <= total) { prefetch_l2((const float4*)q.rast + gn * 32, 512); prefetch_l2(p.dy + gn * 32 * C, 32 * C * 4); }
+        }
+
+        // ---- triangle of the pixel, attribute rows, recomputed texture coordinates
+        const int n = (int)(pidx / hw);
+        int triIdx = in.inb ? float_to_triidx(r.w) - 1 : -1;
+        if (triIdx >= q.T) triIdx = -1;
+        int ai0 = 0, ai1 = 0, ai2 = 0;
+        if (triIdx >= 0)
+        {
+            ai0 = __ldg(q.attr_tri + triIdx * 3); ai1 = __ldg(q.attr_tri + triIdx * 3 + 1); ai2 = __ldg(q.attr_tri + triIdx * 3 + 2);
+            if (ai0 < 0 || ai0 >= q.Va || ai1 < 0 || ai1 >= q.Va || ai2 < 0 || ai2 >= q.Va) triIdx = -1;
+        }
+        const bool valid = triIdx >= 0;
+        const int aoff = q.attr_per_image ? n * q.Va : 0;
+        float4 db = make_float4(0.f, 0.f, 0.f, 0.f);
+        float a0[2] = { 0.f, 0.f }, a1[2] = { 0.f, 0.f }, a2[2] = { 0.f, 0.f };
+        in.uv = make_float2(0.f, 0.f); in.da = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid)
+        {
+            if (q.rast_db) db = ld_stream_f4((const float4*)q.rast_db + pidx);
+            float2 t;
+            t = __ldg((const float2*)q.attr + aoff + ai0); a0[0] = t.x; a0[1] = t.y;
+            t = __ldg((const float2*)q.attr + aoff + ai1); a1[0] = t.x; a1[1] = t.y;
+            t = __ldg((const float2*)q.attr + aoff + ai2); a2[0] = t.x; a2[1] = t.y;
+            interp_uv(r, db, a0, a1, a2, in.uv, in.da);
+            if (!m.has_da) in.da = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+
+        // ---- texture backward of the group: texel gradients are scattered, (g_uv, g_uv_da) stay in registers
+        const TexPixelGrad tg = texgrad_group<C, B, false>(p, m, in, pd, cached, &s_slot[warp], lane, s_stage[warp], hw, trilinear);
+
+        if (!__any_sync(0xffffffffu, valid))            // background group: nothing flows further
+        {
+            if (!RASTER && q.g_rast && in.inb)
+            {
+                st_stream_f4((float4*)q.g_rast + pidx, make_float4(0.f, 0.f, 0.f, 0.f));
+                if (q.g_rast_db) st_stream_f4((float4*)q.g_rast_db + pidx, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+            continue;
+        }
+
+        // ---- interpolate backward (A = 2, all differentials): csrc/common/interpolate.cu:131-274 restated for registers
+        const float y[2] = { valid ? tg.gu : 0.f, valid ? tg.gv : 0.f };
+        const float yd[4] = { valid ? tg.gda.x : 0.f, valid ? tg.gda.y : 0.f, valid ? tg.gda.z : 0.f, valid ? tg.gda.w : 0.f };
+        float2 gr = make_float2(0.f, 0.f);
+        float4 gdb = make_float4(0.f, 0.f, 0.f, 0.f);
+        float t0[2], t1[2], t2[2];
+        {
+            const float b0 = r.x, b1 = r.y, b2 = 1.f - r.x - r.y;
+            #pragma unroll
+            for (int i = 0; i < 2; i++)
+            {
+                const float dsdu = a0[i] - a2[i], dsdv = a1[i] - a2[i];
+                gr.x += y[i] * dsdu; gr.y += y[i] * dsdv;
+                const float dsdx = yd[2 * i], dsdy = yd[2 * i + 1];
+                gdb.x += dsdu * dsdx; gdb.y += dsdu * dsdy; gdb.z += dsdv * dsdx; gdb.w += dsdv * dsdy;
+                const float du = dsdx * db.x + dsdy * db.y, dv = dsdx * db.z + dsdy * db.w;
+                t0[i] = b0 * y[i] + du; t1[i] = b1 * y[i] + dv; t2[i] = b2 * y[i] - du - dv;
+            }
+        }
+        const WarpRuns runs = warp_runs2(valid ? triIdx : -1 - lane, n);     // (triangle, image): a group may straddle two images
+        const bool head = runs.is_head && valid;
+        if (q.g_attr)                                   // warp-uniform
+        {
+            #pragma unroll
+            for (int i = 0; i < 2; i++) { t0[i] = warp_run_sum(t0[i], runs); t1[i] = warp_run_sum(t1[i], runs); t2[i] = warp_run_sum(t2[i], runs); }
+            if (head)
+            {
+                float* ga = q.g_attr + (size_t)aoff * 2;
+                red_add2(ga + 2 * ai0, make_float2(t0[0], t0[1])); red_add2(ga + 2 * ai1, make_float2(t1[0], t1[1])); red_add2(ga + 2 * ai2, make_float2(t2[0], t2[1]));
+            }
+        }
+        if (!RASTER)
+        {
+            if (q.g_rast && in.inb)
+            {
+                st_stream_f4((float4*)q.g_rast + pidx, valid ? make_float4(gr.x, gr.y, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f));
+                if (q.g_rast_db) st_stream_f4((float4*)q.g_rast_db + pidx, valid ? gdb : make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+            continue;
+        }
+
+        // ---- rasterize backward: pm::raster_grad on (g_rast.xy, g_rast_db), one 128-bit reduction per vertex and triangle run
+        if (q.g_pos)                                    // warp-uniform
+        {
+            float gv9[9];
+            #pragma unroll
+            for (int i = 0; i < 9; i++) gv9[i] = 0.f;
+            int vi0 = 0, vi1 = 0, vi2 = 0;
+            bool pv = valid;
+            if (pv)
+            {
+                vi0 = __ldg(q.pos_tri + triIdx * 3); vi1 = __ldg(q.pos_tri + triIdx * 3 + 1); vi2 = __ldg(q.pos_tri + triIdx * 3 + 2);
+                if (vi0 < 0 || vi0 >= q.V || vi1 < 0 || vi1 >= q.V || vi2 < 0 || vi2 >= q.V) pv = false;
+            }
+            // the reference skips pixels whose incoming gradients are all +-0 (csrc/common/rasterize.cu:143-148)
+            const unsigned nz_dy = (__float_as_uint(gr.x) | __float_as_uint(gr.y)) << 1;
+            const unsigned nz_db = q.grad_db ? ((__float_as_uint(gdb.x) | __float_as_uint(gdb.y) | __float_as_uint(gdb.z) | __float_as_uint(gdb.w)) << 1) : 0u;
+            if ((nz_dy | nz_db) == 0u) pv = false;
+            if (pv)
+            {
+                const float4* vb = (const float4*)q.pos + (size_t)n * q.V;
+                const int rp = (int)(pidx - (size_t)n * hw);
+                const int py = rp / p.W, px = rp - py * p.W;
+                const float fx = q.xs * (float)px + q.xo, fy = q.ys * (float)py + q.yo;
+                pm::PixelTri t;
+                pm::pixel_tri(t, __ldg(vb + vi0), __ldg(vb + vi1), __ldg(vb + vi2), fx, fy);
+                float gx[3], gy[3], gw[3];
+                pm::raster_grad<true>(t, fx, fy, q.xs, q.ys, gr.x, gr.y, gdb, nz_db != 0u, gx, gy, gw);
+                #pragma unroll
+                for (int k = 0; k < 3; k++) { gv9[3 * k] = gx[k]; gv9[3 * k + 1] = gy[k]; gv9[3 * k + 2] = gw[k]; }
+            }
+            // runs of the same triangle (the key is the triangle id: attribute and position index buffers may differ)
+            const WarpRuns pruns = warp_runs2(pv ? triIdx : -1 - lane, n);
+            #pragma unroll
+            for (int i = 0; i < 9; i++) gv9[i] = warp_run_sum(gv9[i], pruns);
+            if (pruns.is_head && pv)
+            {
+                float* gp = q.g_pos + (size_t)n * q.V * 4;
+                red_add4(gp + 4 * vi0, make_float4(gv9[0], gv9[1], 0.f, gv9[2]));
+                red_add4(gp + 4 * vi1, make_float4(gv9[3], gv9[4], 0.f, gv9[5]));
+                red_add4(gp + 4 * vi2, make_float4(gv9[6], gv9[7], 0.f, gv9[8]));
+            }
+        }
     }
     pending_flush<C>(pd, p, lane);
 }
@@ -1194,9 +1415,9 @@ static __device__ __forceinline__ float2 cube_index_linear(const TexParams& p, f
 }
 
 // four taps with the corner rule: the missing texel is the average of the other three (texture_kernel.cu:590-612)
-static __device__ __forceinline__ void cube_fetch(const float* t, int4 tc, bool corner, float4& a, float4& b, float4& c, float4& d)
+static __device__ __forceinline__ void cube_fetch(const float* t, int4 tc, bool corner, float4& a, float4& b, float4& c, float4& d, int Cp = 4, int k = 0)
 {
-    a = texel4(t, tc.x, 4, 0); b = texel4(t, tc.y, 4, 0); c = texel4(t, tc.z, 4, 0); d = texel4(t, tc.w, 4, 0);
+    a = texel4(t, tc.x, Cp, k); b = texel4(t, tc.y, Cp, k); c = texel4(t, tc.z, Cp, k); d = texel4(t, tc.w, Cp, k);
     if (corner)
     {
         float4 avg = make_float4((a.x + b.x + c.x + d.x) * 0.33333333f, (a.y + b.y + c.y + d.y) * 0.33333333f,
@@ -1376,6 +1597,153 @@ __global__ void __launch_bounds__(256) texture_cube_grad_kernel(const TexParams 
     }
 }
 
+// ---- cube maps with any channel count: same addressing, the texel is walked in 128-bit channel groups of the padded
+// pyramid (the reference serves every channel count through vector widths 1/2/4, csrc/torch/torch_texture.cpp:344-401).
+__global__ void __launch_bounds__(256) texture_cube_fwd_generic(const TexParams p)
+{
+    const TexMode m = tex_mode(p);
+    const size_t hw = (size_t)p.H * p.W, total = hw * p.N;
+    const int C = p.C, Cp = p.Cp;
+    for (size_t pidx = (size_t)blockIdx.x * 256 + threadIdx.x; pidx < total; pidx += (size_t)gridDim.x * 256)
+    {
+        int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
+        float3 v, dX, dY;
+        cube_load_dirs(p, pidx, v, dX, dY);
+        float* o = p.out + pidx * C;
+        if (m.filter == B200DR_FILTER_NEAREST)
+        {
+            int tc = cube_nearest(p, v, tz);
+            for (int k = 0; k < Cp; k += 4) put4(o, k, C, texel4(p.tex[0], tc, Cp, k));
+            continue;
+        }
+        int level0, level1; float flevel; float4 dw;
+        float bias = p.bias ? ld_stream_f(p.bias + pidx) : 0.f;
+        mip_level_from<false>(p, m, cube_grad_st(v, dX, dY), bias, level0, level1, flevel, dw);
+        int4 tc0, tc1 = make_int4(-1, -1, -1, -1); bool cor0, cor1 = false;
+        float2 uv0 = cube_index_linear(p, v, tz, level0, tc0, cor0), uv1 = make_float2(0.f, 0.f);
+        const bool two = (m.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && flevel > 0.f);
+        if (two) uv1 = cube_index_linear(p, v, tz, level1, tc1, cor1);
+        for (int k = 0; k < Cp; k += 4)
+        {
+            float4 a, b, c, d;
+            cube_fetch(p.tex[level0], tc0, cor0, a, b, c, d, Cp, k);
+            float4 r = bilerp4(a, b, c, d, uv0);
+            if (two)
+            {
+                cube_fetch(p.tex[level1], tc1, cor1, a, b, c, d, Cp, k);
+                float4 r1 = bilerp4(a, b, c, d, uv1);
+                r = make_float4(lerpf(r.x, r1.x, flevel), lerpf(r.y, r1.y, flevel), lerpf(r.z, r1.z, flevel), lerpf(r.w, r1.w, flevel));
+            }
+            put4(o, k, C, r);
+        }
+    }
+}
+
+static __device__ __forceinline__ void scatter_group(float* g, int tc, int Cp, int k, float w, float4 dy)
+{
+    if (tc < 0) return;
+    red_add4(g + (size_t)tc * Cp + k, make_float4(w * dy.x, w * dy.y, w * dy.z, w * dy.w));
+}
+
+__global__ void __launch_bounds__(256) texture_cube_grad_generic(const TexParams p)
+{
+    const TexMode m = tex_mode(p);
+    const size_t hw = (size_t)p.H * p.W, total = hw * p.N;
+    const bool trilinear = (m.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
+    const int C = p.C, Cp = p.Cp;
+    for (size_t pidx = (size_t)blockIdx.x * 256 + threadIdx.x; pidx < total; pidx += (size_t)gridDim.x * 256)
+    {
+        const float* pdy = p.dy + pidx * C;
+        unsigned dmax = 0u;
+        for (int i = 0; i < C; i++) dmax |= __float_as_uint(pdy[i]);
+        float3 g_v = make_float3(0.f, 0.f, 0.f), g0 = g_v, g1 = g_v;
+        float df = 0.f;
+        if (__uint_as_float(dmax) != 0.f)
+        {
+            int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
+            float3 v, dX, dY;
+            cube_load_dirs(p, pidx, v, dX, dY);
+            if (m.filter == B200DR_FILTER_NEAREST)
+            {
+                int tc = cube_nearest(p, v, tz);
+                for (int k = 0; k < Cp; k += 4)
+                    scatter_group(p.gpad[0], tc, Cp, k, 1.f, make_float4(pdy[k], (k + 1 < C) ? pdy[k + 1] : 0.f, (k + 2 < C) ? pdy[k + 2] : 0.f, (k + 3 < C) ? pdy[k + 3] : 0.f));
+            }
+            else
+            {
+                int level0, level1; float flevel; float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
+                float bias = p.bias ? ld_stream_f(p.bias + pidx) : 0.f;
+                mip_level_from<true>(p, m, cube_grad_st(v, dX, dY), bias, level0, level1, flevel, dw);
+                float3 dfdv = make_float3(0.f, 0.f, 0.f);
+                if (trilinear && p.uv_da)
+                {
+                    dfdv = cube_grad2_dot(v, dX, dY, dw);
+                    if (!isfinite(dfdv.x) || !isfinite(dfdv.y) || !isfinite(dfdv.z)) { dfdv = make_float3(0.f, 0.f, 0.f); dw = make_float4(0.f, 0.f, 0.f, 0.f); }
+                }
+                const bool two = trilinear && (flevel > 0.f);
+                const float f0 = trilinear ? (1.f - flevel) : 1.f;
+                float gu = 0.f, gv = 0.f;
+                int4 tc0, tc1 = make_int4(-1, -1, -1, -1); bool cor0, cor1 = false;
+                float2 uv0 = cube_index_linear(p, v, tz, level0, tc0, cor0), uv1 = make_float2(0.f, 0.f);
+                if (two) uv1 = cube_index_linear(p, v, tz, level1, tc1, cor1);
+                float uv011 = uv0.x * uv0.y, uv010 = uv0.x - uv011, uv001 = uv0.y - uv011, uv000 = 1.f - uv0.x - uv001;
+                const float4 w0 = cube_weights(make_float4(uv000 * f0, uv010 * f0, uv001 * f0, uv011 * f0), tc0, cor0);
+                float uv111 = uv1.x * uv1.y, uv110 = uv1.x - uv111, uv101 = uv1.y - uv111, uv100 = 1.f - uv1.x - uv101;
+                const float4 w1 = cube_weights(make_float4(uv100 * flevel, uv110 * flevel, uv101 * flevel, uv111 * flevel), tc1, cor1);
+                const float sclu0 = (float)lvl_w(p, level0), sclu1 = (float)lvl_w(p, level1);
+                for (int k = 0; k < Cp; k += 4)
+                {
+                    const float4 dy4 = make_float4(pdy[k], (k + 1 < C) ? pdy[k + 1] : 0.f, (k + 2 < C) ? pdy[k + 2] : 0.f, (k + 3 < C) ? pdy[k + 3] : 0.f);
+                    float* gp0 = p.gpad[level0];
+                    scatter_group(gp0, tc0.x, Cp, k, w0.x, dy4); scatter_group(gp0, tc0.y, Cp, k, w0.y, dy4);
+                    scatter_group(gp0, tc0.z, Cp, k, w0.z, dy4); scatter_group(gp0, tc0.w, Cp, k, w0.w, dy4);
+                    float4 A00, A10, A01, A11, B00, B10, B01, B11;
+                    cube_fetch(p.tex[level0], tc0, cor0, A00, A10, A01, A11, Cp, k);
+                    if (two)
+                    {
+                        float* gp1 = p.gpad[level1];
+                        scatter_group(gp1, tc1.x, Cp, k, w1.x, dy4); scatter_group(gp1, tc1.y, Cp, k, w1.y, dy4);
+                        scatter_group(gp1, tc1.z, Cp, k, w1.z, dy4); scatter_group(gp1, tc1.w, Cp, k, w1.w, dy4);
+                        cube_fetch(p.tex[level1], tc1, cor1, B00, B10, B01, B11, Cp, k);
+                    }
+                    #pragma unroll
+                    for (int j = 0; j < 4; j++)
+                    {
+                        if (k + j >= C) break;
+                        const float dyc = (&dy4.x)[j];
+                        const float a00 = (&A00.x)[j], a10 = (&A10.x)[j], a01 = (&A01.x)[j], a11 = (&A11.x)[j];
+                        const float ad = (a11 + a00 - a10 - a01), dy0 = f0 * dyc;
+                        gu += dy0 * ((a10 - a00) + uv0.y * ad) * sclu0;
+                        gv += dy0 * ((a01 - a00) + uv0.x * ad) * sclu0;
+                        if (two)
+                        {
+                            const float b00 = (&B00.x)[j], b10 = (&B10.x)[j], b01 = (&B01.x)[j], b11 = (&B11.x)[j];
+                            const float bd = (b11 + b00 - b10 - b01), dy1 = flevel * dyc;
+                            gu += dy1 * ((b10 - b00) + uv1.y * bd) * sclu1;
+                            gv += dy1 * ((b01 - b00) + uv1.x * bd) * sclu1;
+                            df += (bilerp(b00, b10, b01, b11, uv1) - bilerp(a00, a10, a01, a11, uv0)) * dyc;
+                        }
+                    }
+                }
+                g_v = cube_grad(v, gu, gv);
+                if (trilinear) { g_v.x += dfdv.x * df; g_v.y += dfdv.y * df; g_v.z += dfdv.z * df; }
+                if (trilinear && p.uv_da)
+                {
+                    g0 = cube_grad(v, dw.x * df, dw.z * df);
+                    g1 = cube_grad(v, dw.y * df, dw.w * df);
+                }
+            }
+        }
+        if (p.g_uv) { p.g_uv[pidx * 3] = g_v.x; p.g_uv[pidx * 3 + 1] = g_v.y; p.g_uv[pidx * 3 + 2] = g_v.z; }
+        if (p.g_bias) p.g_bias[pidx] = df;
+        if (p.g_uv_da)
+        {
+            float2* q = (float2*)p.g_uv_da + pidx * 3;
+            q[0] = make_float2(g0.x, g1.x); q[1] = make_float2(g0.y, g1.y); q[2] = make_float2(g0.z, g1.z);
+        }
+    }
+}
+
 // Resolve: g_out[texel][c] = pad[0][texel][c] (+ sum over levels of weight * pad[L][parent texel][c] when pulling mips),
 // written in the caller's C-channel layout.  Pull weights as in MipGradKernel (texture_kernel.cu:843-900).
 struct ResolveParams
@@ -1421,7 +1789,6 @@ static int tex_fill(TexParams& p, const char* fn, const float* tex, const float*
     B200DR_CHECK(filter >= 0 && filter < 4, "%s: filter_mode unsupported", fn);
     B200DR_CHECK(boundary >= 0 && boundary < 4, "%s: boundary_mode unsupported", fn);
     const bool cube = (boundary == B200DR_BOUNDARY_CUBE);
-    B200DR_CHECK(!cube || C <= 4, "%s: cube map mode supports at most 4 channels in this build", fn);
     B200DR_CHECK(!cube || texW == texH, "%s: texture shape must be square in cube map mode", fn);
     B200DR_CHECK(N > 0 && H > 0 && W > 0, "%s: uv must have shape [>0, >0, >0, %d]", fn, cube ? 3 : 2);
     B200DR_CHECK(texD > 0 && texH > 0 && texW > 0 && C > 0, "%s: tex must have shape[>0, >0, >0, >0]", fn);
@@ -1574,6 +1941,7 @@ extern "C" int b200dr_texture_fwd(const float* tex, const float* const* mip_ptrs
         case 2: texture_cube_fwd_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(p); break;
         case 3: texture_cube_fwd_kernel<3><<<(unsigned)blocks, 256, 0, stream>>>(p); break;
         case 4: texture_cube_fwd_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(p); break;
+        default: texture_cube_fwd_generic<<<(unsigned)blocks, 256, 0, stream>>>(p); break;
         }
         B200DR_CHECK_LAUNCH("texture_fwd()");
         return 0;
@@ -1656,6 +2024,7 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
         case 2: texture_cube_grad_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(p); break;
         case 3: texture_cube_grad_kernel<3><<<(unsigned)blocks, 256, 0, stream>>>(p); break;
         case 4: texture_cube_grad_kernel<4><<<(unsigned)blocks, 256, 0, stream>>>(p); break;
+        default: texture_cube_grad_generic<<<(unsigned)blocks, 256, 0, stream>>>(p); break;
         }
     }
     else if (C <= 4 && B200DR_ALIGNED16(dy))
@@ -1699,6 +2068,93 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
     }
     b200dr_count_launches(-1);              // the check below counts one
     B200DR_CHECK_LAUNCH("texture_grad(resolve)");
+    return 0;
+}
+
+template <int F, int B, bool RASTER>
+static void launch_chain_grad_c(const TexParams& p, const ChainParams& q, unsigned blocks, cudaStream_t stream)
+{
+    switch (p.C) {
+    case 1: texture_chain_grad_fast<1, F, B, RASTER><<<blocks, TEXG_THREADS, 0, stream>>>(p, q); break;
+    case 2: texture_chain_grad_fast<2, F, B, RASTER><<<blocks, TEXG_THREADS, 0, stream>>>(p, q); break;
+    case 3: texture_chain_grad_fast<3, F, B, RASTER><<<blocks, TEXG_THREADS, 0, stream>>>(p, q); break;
+    case 4: texture_chain_grad_fast<4, F, B, RASTER><<<blocks, TEXG_THREADS, 0, stream>>>(p, q); break;
+    }
+}
+template <bool RASTER>
+static void launch_chain_grad(const TexParams& p, const ChainParams& q, unsigned blocks, cudaStream_t stream)
+{
+    const int f = p.filter, b = p.boundary;
+    if      (f == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && b == B200DR_BOUNDARY_WRAP)  launch_chain_grad_c<B200DR_FILTER_LINEAR_MIPMAP_LINEAR, B200DR_BOUNDARY_WRAP, RASTER>(p, q, blocks, stream);
+    else if (f == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && b == B200DR_BOUNDARY_CLAMP) launch_chain_grad_c<B200DR_FILTER_LINEAR_MIPMAP_LINEAR, B200DR_BOUNDARY_CLAMP, RASTER>(p, q, blocks, stream);
+    else                                                                            launch_chain_grad_c<-1, -1, RASTER>(p, q, blocks, stream);
+}
+
+// Fused backward of texture(interpolate(attr, rasterize(pos))): see texture_chain_grad_fast.  Extension of the op surface (the
+// reference has no counterpart); the front end uses it only when it can prove the provenance of uv / uv_da, see
+// nvdiffrast_b200/torch/ops.py (_fusable) and INTEGRATION.md.
+extern "C" int b200dr_texture_chain_grad(const float* tex, const float* const* mip_ptrs, int max_level, const float* dy,
+                                         const float* attr, const int32_t* attr_tri, int Va, int attr_per_image,
+                                         const float* rast, const float* rast_db,
+                                         const float* pos, const int32_t* pos_tri, int V, int grad_db,
+                                         int N, int H, int W, int T, int texD, int texH, int texW, int C,
+                                         int filter_mode, int boundary_mode,
+                                         float* g_tex, float* g_attr, float* g_rast, float* g_rast_db, float* g_pos,
+                                         void* scratch, size_t scratch_bytes, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const char* fn = "texture_chain_grad()";
+    B200DR_CHECK(boundary_mode != B200DR_BOUNDARY_CUBE && C >= 1 && C <= 4, "%s: 2-D textures with at most 4 channels only", fn);
+    B200DR_CHECK(filter_mode == B200DR_FILTER_LINEAR || filter_mode == B200DR_FILTER_LINEAR_MIPMAP_LINEAR || filter_mode == B200DR_FILTER_LINEAR_MIPMAP_NEAREST,
+                 "%s: filter_mode unsupported", fn);
+    const bool mip = (filter_mode != B200DR_FILTER_LINEAR);
+    B200DR_CHECK(!mip || rast_db, "%s: mipmapped filtering needs rast_db (pixel differentials of the attributes)", fn);
+    B200DR_CHECK(attr && attr_tri && rast && dy && Va > 0 && T > 0, "%s: missing input", fn);
+    B200DR_CHECK(B200DR_ALIGNED16(rast) && B200DR_ALIGNED16(rast_db) && B200DR_ALIGNED16(dy) && (((uintptr_t)attr) & 7) == 0, "%s: input tensor misaligned", fn);
+    B200DR_CHECK(!pos || (pos_tri && V > 0 && B200DR_ALIGNED16(pos)), "%s: pos / tri missing or misaligned", fn);
+    B200DR_CHECK(B200DR_ALIGNED16(g_rast) && B200DR_ALIGNED16(g_rast_db) && (!g_rast || g_rast_db || !rast_db), "%s: g_rast outputs missing or misaligned", fn);
+    B200DR_CHECK((((uintptr_t)g_attr) & 7) == 0 && B200DR_ALIGNED16(g_pos), "%s: gradient output misaligned", fn);
+    TexParams p = {};
+    // uv is recomputed in the kernel; a non-null placeholder tells the mode helpers that pixel differentials exist
+    if (tex_fill(p, fn, tex, mip_ptrs, max_level, 0, mip ? rast_db : 0, 0, N, H, W, texD, texH, texW, C, filter_mode, boundary_mode)) return 1;
+    p.dy = dy; p.tile2d = 0;
+    size_t need = b200dr_texture_grad_scratch_bytes(texD, texH, texW, C, p.mip_max);
+    B200DR_CHECK(scratch && scratch_bytes >= need && B200DR_ALIGNED16(scratch), "%s: scratch buffer too small or misaligned", fn);
+    if (cudaMemsetAsync(scratch, 0, need, stream) != cudaSuccess) { b200dr_set_error("%s: cudaMemsetAsync failed", fn); return 1; }
+    ResolveParams r = {};
+    {
+        char* s = (char*)scratch;
+        for (int L = 0; L <= p.mip_max; L++)
+        {
+            size_t w = (texW >> L) > 1 ? (texW >> L) : 1, h = (texH >> L) > 1 ? (texH >> L) : 1;
+            p.gpad[L] = (float*)s; r.gpad[L] = (const float*)s;
+            s += w * h * texD * p.Cp * sizeof(float);
+        }
+    }
+    ChainParams q = {};
+    q.rast = rast; q.rast_db = rast_db; q.attr = attr; q.attr_tri = attr_tri; q.pos = pos; q.pos_tri = pos_tri;
+    q.g_attr = g_attr; q.g_pos = g_pos; q.g_rast = g_rast; q.g_rast_db = g_rast_db;
+    q.Va = Va; q.V = V; q.T = T; q.attr_per_image = attr_per_image; q.grad_db = grad_db;
+    q.xs = 2.f / (float)W; q.xo = 1.f / (float)W - 1.f; q.ys = 2.f / (float)H; q.yo = 1.f / (float)H - 1.f;
+
+    size_t groups = ((size_t)N * H * W + 31) / 32;
+    size_t blocks = (groups + (TEXG_THREADS / 32) - 1) / (TEXG_THREADS / 32);
+    size_t bcap = (size_t)b200dr_num_sms() * TCG_MINB * 4;
+    if (blocks > bcap) blocks = bcap;
+    if (pos) launch_chain_grad<true>(p, q, (unsigned)blocks, stream);
+    else     launch_chain_grad<false>(p, q, (unsigned)blocks, stream);
+    B200DR_CHECK_LAUNCH(fn);
+
+    r.C = C; r.Cp = p.Cp; r.texD = texD; r.mip_max = p.mip_max; r.baseW = texW; r.baseH = texH;
+    r.level = 0; r.texW = texW; r.texH = texH; r.pull = (p.mip_max > 0) ? 1 : 0; r.g_out = g_tex;
+    if (g_tex)
+    {
+        size_t total = (size_t)texW * texH * texD * C;
+        size_t rb = (total + 255) / 256, rcap = (size_t)b200dr_num_sms() * 16;
+        if (rb > rcap) rb = rcap;
+        texture_grad_resolve_kernel<<<(unsigned)rb, 256, 0, stream>>>(r);
+        B200DR_CHECK_LAUNCH("texture_chain_grad(resolve)");
+    }
     return 0;
 }
 

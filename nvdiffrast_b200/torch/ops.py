@@ -6,6 +6,7 @@ reference's C++ binding layer did (csrc/torch/torch_*.cpp): input validation, ou
 allocator, current-stream lookup.  There is no CPU path and no fallback: CPU tensors raise, a missing CUDA library raises.
 """
 import ctypes
+import os
 import warnings
 
 import numpy as np
@@ -66,6 +67,50 @@ def _require(cond, fn, msg):
 
 # ----------------------------------------------------------------------------------------------
 # Log level (nvdiffrast/torch/ops.py:18-41).
+
+
+# ----------------------------------------------------------------------------------------------
+# Cross-op fusion behind the unchanged API.
+#
+# The op boundaries force the backward pass to write g_uv / g_uv_da / g_rast / g_rast_db to HBM only to read them straight
+# back in the next op.  `rasterize()` and `interpolate()` therefore tag their output tensors with where they came from; when
+# `texture()` is handed tensors that are provably the untouched outputs of interpolate(attr, rast, tri, rast_db, 'all') -- and
+# those the untouched outputs of rasterize(pos, ...) -- it samples exactly as before but registers ONE backward node that
+# carries the gradient from the colour all the way to (tex, attr, pos) in a single kernel (b200dr_texture_chain_grad).  It
+# reads uv / uv_da as constants, so the interpolate / rasterize nodes receive no gradient from this path and are not even
+# executed unless another consumer (antialias's own pos gradient is separate) needs them; autograd sums the paths as usual.
+# Anything the proof does not cover (views, in-place edits, hooks or retain_grad on the intermediates, custom mip stacks,
+# mip_level_bias, cube maps, more than 4 channels, attribute counts other than 2) takes the op-by-op path.
+
+_fusion_enabled = os.environ.get("B200DR_FUSION", "1") not in ("0", "false", "off")
+
+
+def set_fusion(enabled):
+    """Enable / disable the fused texture -> interpolate -> rasterize backward (default: enabled; env B200DR_FUSION=0)."""
+    global _fusion_enabled
+    _fusion_enabled = bool(enabled)
+
+
+def get_fusion():
+    return _fusion_enabled
+
+
+class _Provenance:
+    """Attached to op outputs as `_b200dr_prov` (outputs reference the record, the record references only the op's inputs:
+    no reference cycle).  `versions`: in-place version counters of the outputs when they were produced."""
+    __slots__ = ("kind", "inputs", "versions", "meta")
+
+    def __init__(self, kind, inputs, outputs, **meta):
+        self.kind, self.inputs, self.meta = kind, inputs, meta
+        self.versions = tuple(o._version for o in outputs)
+        for o in outputs:
+            o._b200dr_prov = self
+
+
+def _pristine(t, prov, slot):
+    """t is output `slot` of the op recorded in prov, unmodified, and nobody watches its gradient."""
+    return (getattr(t, "_b200dr_prov", None) is prov and t._version == prov.versions[slot]
+            and not t.retains_grad and not getattr(t, "_backward_hooks", None))
 
 
 def get_log_level():
@@ -241,7 +286,9 @@ def rasterize(glctx, pos, tri, resolution, ranges=None, grad_db=True):
     if glctx.active_depth_peeler is not None:
         # The reference *returns* this error object (nvdiffrast/torch/ops.py:131-132); kept for drop-in behaviour.
         return RuntimeError("Cannot call rasterize() during depth peeling operation, use rasterize_next_layer() instead")
-    return _rasterize_func.apply(glctx, pos, tri, resolution, ranges, grad_db, -1)
+    rast, rast_db = _rasterize_func.apply(glctx, pos, tri, resolution, ranges, grad_db, -1)
+    _Provenance("rasterize", (pos, tri), (rast, rast_db), grad_db=grad_db)
+    return rast, rast_db
 
 
 class DepthPeeler:
@@ -285,6 +332,7 @@ class DepthPeeler:
         assert self.raster_ctx.active_depth_peeler is self
         assert self.peeling_idx >= 0
         result = _rasterize_func.apply(self.raster_ctx, self.pos, self.tri, self.resolution, self.ranges, self.grad_db, self.peeling_idx)
+        _Provenance("rasterize", (self.pos, self.tri), result, grad_db=self.grad_db)
         self.peeling_idx += 1
         return result
 
@@ -413,8 +461,12 @@ def interpolate(attr, rast, tri, rast_db=None, diff_attrs=None):
     assert all(isinstance(x, torch.Tensor) for x in (attr, rast, tri))
     if diff_attrs:
         assert isinstance(rast_db, torch.Tensor)
-        return _interpolate_func_da.apply(attr, rast, tri, rast_db, diff_attrs_all, diff_attrs_list)
-    return _interpolate_func.apply(attr, rast, tri)
+        out = _interpolate_func_da.apply(attr, rast, tri, rast_db, diff_attrs_all, diff_attrs_list)
+        _Provenance("interpolate", (attr, rast, tri, rast_db), out, diff_all=bool(diff_attrs_all))
+        return out
+    out = _interpolate_func.apply(attr, rast, tri)
+    _Provenance("interpolate", (attr, rast, tri, None), out, diff_all=False)
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -508,8 +560,6 @@ def _tex_setup(fn, tex, uv, uv_da, mip_level_bias, mip_wrapper, mip_stack, filte
         _require(uv.dim() == 4 and min(uv.shape[:3]) > 0 and uv.shape[3] == 3, fn, "uv must have shape [>0, >0, >0, 3] in cube map mode")
         _require(tex.shape[2] == tex.shape[3], fn, "texture shape must be square in cube map mode")
         D, Ht, Wt, C = tex.shape[0], tex.shape[2], tex.shape[3], tex.shape[4]
-        if C > 4:
-            raise NotImplementedError("nvdiffrast_b200: cube map textures support at most 4 channels in this build")
     else:
         _require(tex.dim() == 4 and min(tex.shape) > 0, fn, "tex must have shape[>0, >0, >0, >0]")
         _require(uv.dim() == 4 and min(uv.shape[:3]) > 0 and uv.shape[3] == 2, fn, "uv must have shape [>0, >0, >0, 2]")
@@ -649,6 +699,100 @@ class _texture_func(torch.autograd.Function):
         return None, g_tex, None, None, None
 
 
+def _fusion_plan(tex, uv, uv_da, mip_level_bias, mip_stack, filter_mode, boundary_mode):
+    """-> dict describing the fused backward, or None when the op-by-op path must be taken (see the comment at the top)."""
+    if not (_fusion_enabled and torch.is_grad_enabled()) or boundary_mode == 'cube' or mip_level_bias is not None or mip_stack:
+        return None
+    if filter_mode not in ('linear', 'linear-mipmap-nearest', 'linear-mipmap-linear'):
+        return None
+    if not (tex.is_cuda and tex.dim() == 4 and tex.shape[-1] <= 4 and tex.dtype == torch.float32):
+        return None
+    prov = getattr(uv, "_b200dr_prov", None)
+    if prov is None or prov.kind != "interpolate" or not _pristine(uv, prov, 0):
+        return None
+    mip = 'mipmap' in filter_mode
+    attr, rast, attr_tri, rast_db = prov.inputs
+    if mip:
+        if uv_da is None or not prov.meta["diff_all"] or rast_db is None or not _pristine(uv_da, prov, 1):
+            return None
+    elif uv_da is not None:
+        return None
+    if attr.shape[-1] != 2 or attr.dtype != torch.float32 or not attr.is_contiguous():
+        return None
+    if not (uv.requires_grad or tex.requires_grad):
+        return None
+    plan = dict(attr=attr, attr_tri=attr_tri, rast=rast, rast_db=rast_db if mip else None, pos=None, pos_tri=None, grad_db=False,
+                attr_per_image=bool(attr.dim() == 3 and attr.shape[0] > 1))
+    rprov = getattr(rast, "_b200dr_prov", None)
+    if (rprov is not None and rprov.kind == "rasterize" and _pristine(rast, rprov, 0) and rprov.inputs[0].dim() == 3
+            and (rast_db is None or not mip or _pristine(rast_db, rprov, 1))):
+        plan.update(pos=rprov.inputs[0], pos_tri=rprov.inputs[1], grad_db=bool(rprov.meta["grad_db"]))
+    return plan
+
+
+def _texture_chain_grad(tex, dy, mip_wrapper, filter_mode, boundary_mode, attr, attr_tri, rast, rast_db, pos, pos_tri, grad_db,
+                        attr_per_image, need_tex, need_attr, need_pos, need_rast):
+    """Host side of b200dr_texture_chain_grad (include/b200dr.h): -> (g_tex, g_attr, g_pos, g_rast, g_rast_db)."""
+    fn = "texture_chain_grad"
+    lib = _lib.load()
+    dev = _check_inputs(fn, f32=[("tex", tex), ("attr", attr), ("rast", rast), ("rast_db", rast_db), ("pos", pos)], i32=[("tri", attr_tri), ("pos_tri", pos_tri)])
+    _check_inputs(fn, f32=[("tex", tex), ("dy", dy)], contiguous=False)
+    N, H, W = rast.shape[0], rast.shape[1], rast.shape[2]
+    D, Ht, Wt, C = tex.shape
+    _require(tuple(dy.shape) == (N, H, W, C), fn, "dy must have shape [minibatch_size, height, width, channels]")
+    dy = dy.contiguous()
+    enable_mip = filter_mode in (2, 3)
+    Cp = (C + 3) & ~3
+    level_max = 0
+    ptrs = (ctypes.c_void_p * (_TEX_MAX_MIP_LEVEL + 1))()
+    with torch.cuda.device(dev):
+        keep = _tex_pad(tex)
+        if enable_mip:
+            total, offs, level_max = _mip_info(fn, (D, Ht, Wt, Cp), mip_wrapper.max_mip_level)
+            base = mip_wrapper.mip.data_ptr()
+            for i in range(1, level_max + 1):
+                ptrs[i] = base + 4 * offs[i]
+        Va = attr.shape[-2]
+        use_pos = pos is not None and need_pos                  # carry the gradient through rasterize's backward as well
+        g_tex = torch.empty_like(tex) if need_tex else None
+        g_attr = torch.zeros_like(attr) if need_attr else None
+        g_pos = torch.zeros_like(pos) if use_pos else None
+        g_rast = torch.empty_like(rast) if (not use_pos and need_rast) else None
+        g_rast_db = torch.empty_like(rast_db) if (g_rast is not None and rast_db is not None) else None
+        nbytes = lib.b200dr_texture_grad_scratch_bytes(D, Ht, Wt, C, level_max)
+        scratch = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        _lib.call("b200dr_texture_chain_grad", _ptr(keep), ptrs, level_max, _ptr(dy),
+                  _ptr(attr), _ptr(attr_tri), Va, int(attr_per_image), _ptr(rast), _ptr(rast_db),
+                  _ptr(pos) if use_pos else None, _ptr(pos_tri) if use_pos else None, pos.shape[1] if use_pos else 0, int(grad_db),
+                  N, H, W, attr_tri.shape[0], D, Ht, Wt, C, filter_mode, boundary_mode,
+                  _ptr(g_tex), _ptr(g_attr), _ptr(g_rast), _ptr(g_rast_db), _ptr(g_pos), _ptr(scratch), nbytes, _stream(dev))
+    return g_tex, g_attr, g_pos, g_rast, g_rast_db
+
+
+class _texture_chain_func(torch.autograd.Function):
+    """texture() whose backward runs the fused chain kernel.  Differentiable inputs: tex, attr and either pos (rasterize's
+    outputs proven pristine) or rast / rast_db; uv and uv_da enter as constants."""
+
+    @staticmethod
+    def forward(ctx, tex, attr, pos, rast, rast_db, uv, uv_da, mip_wrapper, filter_mode_enum, boundary_mode_enum, plan):
+        out = _texture_fwd(tex, uv, uv_da, None, mip_wrapper, (), filter_mode_enum, boundary_mode_enum)
+        empty = torch.tensor([])
+        ctx.save_for_backward(tex, attr, plan["attr_tri"], plan["rast"], plan["rast_db"] if plan["rast_db"] is not None else empty,
+                              plan["pos"] if plan["pos"] is not None else empty, plan["pos_tri"] if plan["pos_tri"] is not None else empty)
+        ctx.saved_misc = mip_wrapper, filter_mode_enum, boundary_mode_enum, plan["grad_db"], plan["attr_per_image"], plan["rast_db"] is not None, plan["pos"] is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        tex, attr, attr_tri, rast, rast_db, pos, pos_tri = ctx.saved_tensors
+        mip_wrapper, fm, bm, grad_db, attr_per_image, has_db, has_pos = ctx.saved_misc
+        need = ctx.needs_input_grad
+        g_tex, g_attr, g_pos, g_rast, g_rast_db = _texture_chain_grad(
+            tex, dy, mip_wrapper, fm, bm, attr, attr_tri, rast, rast_db if has_db else None, pos if has_pos else None, pos_tri if has_pos else None,
+            grad_db, attr_per_image, need[0], need[1], need[2], need[3] or need[4])
+        return (g_tex, g_attr, g_pos, g_rast if need[3] else None, g_rast_db if need[4] else None, None, None, None, None, None, None)
+
+
 def texture(tex, uv, uv_da=None, mip_level_bias=None, mip=None, filter_mode='auto', boundary_mode='wrap', max_mip_level=None):
     """Perform texture sampling.
 
@@ -682,8 +826,8 @@ def texture(tex, uv, uv_da=None, mip_level_bias=None, mip=None, filter_mode='aut
     filter_mode_enum = _FILTER_MODES[filter_mode]
     boundary_mode_enum = _BOUNDARY_MODES[boundary_mode]
 
+    mip_wrapper, mip_stack = None, []
     if 'mipmap' in filter_mode:
-        mip_wrapper, mip_stack = None, []
         if mip is not None:
             assert isinstance(mip, (TextureMipWrapper, list))
             if isinstance(mip, list):
@@ -693,6 +837,15 @@ def texture(tex, uv, uv_da=None, mip_level_bias=None, mip=None, filter_mode='aut
                 mip_wrapper = mip
         else:
             mip_wrapper = _texture_construct_mip(tex, max_mip_level, boundary_mode == 'cube')
+    plan = _fusion_plan(tex, uv, uv_da if 'mipmap' in filter_mode else None, mip_level_bias, mip_stack, filter_mode, boundary_mode)
+    if plan is not None:
+        # the intermediates enter as constants (detached): the fused node owns the whole path colour -> (tex, attr, pos)
+        if plan["pos"] is not None:
+            return _texture_chain_func.apply(tex, plan["attr"], plan["pos"], plan["rast"].detach(), None, uv.detach(),
+                                             uv_da.detach() if 'mipmap' in filter_mode else None, mip_wrapper, filter_mode_enum, boundary_mode_enum, plan)
+        return _texture_chain_func.apply(tex, plan["attr"], None, plan["rast"], plan["rast_db"], uv.detach(),
+                                         uv_da.detach() if 'mipmap' in filter_mode else None, mip_wrapper, filter_mode_enum, boundary_mode_enum, plan)
+    if 'mipmap' in filter_mode:
         return _texture_func_mip.apply(filter_mode, tex, uv, uv_da, mip_level_bias, mip_wrapper, filter_mode_enum, boundary_mode_enum, *mip_stack)
     return _texture_func.apply(filter_mode, tex, uv, filter_mode_enum, boundary_mode_enum)
 

@@ -86,7 +86,15 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_device():
     assert tex_fwd(1, 1, C=0) != 0 and "tex must have shape" in err()
     assert tex_fwd(1, 1, D=2, N=3) != 0 and "minibatch size mismatch" in err()
     assert tex_fwd(3, 1) != 0 and "requires uv_da and/or mip_level_bias" in err()
-    assert tex_fwd(1, 0, C=5) != 0 and "at most 4 channels" in err()
+    # fused chain backward (extension): cube maps / wide textures / missing pixel differentials are refused on the host
+    def chain(filter_mode=3, boundary_mode=1, C=3, rast_db=vp(256), pos=None):
+        return lib.b200dr_texture_chain_grad(vp(256), ptrs, 0, vp(256), vp(256), vp(256), 8, 0, vp(256), rast_db, pos, None, 0, 1,
+                                             1, 4, 4, 2, 1, 8, 8, C, filter_mode, boundary_mode, vp(256), vp(256), vp(256), vp(256), None, vp(256), 1 << 20, None)
+    assert chain(boundary_mode=0) != 0 and "at most 4 channels" in err()
+    assert chain(C=5) != 0 and "at most 4 channels" in err()
+    assert chain(filter_mode=0) != 0 and "filter_mode unsupported" in err()
+    assert chain(rast_db=None) != 0 and "needs rast_db" in err()
+    assert chain(pos=vp(256)) != 0 and "pos / tri missing" in err()
     assert tex_fwd(1, 0, Ht=8, Wt=16) != 0 and "square in cube map mode" in err()
     assert tex_fwd(1, 1, uv=vp(260)) != 0 and "not aligned" in err()
     # rasterize

@@ -201,6 +201,8 @@ CUBE_CASES = [  # filter_mode, use_da, use_bias, channels, texture minibatch, fa
     ("linear-mipmap-linear", True, False, 4, 2, 16),
     ("linear-mipmap-linear", True, True, 1, 1, 8),
     ("linear-mipmap-linear", False, True, 3, 1, 16),
+    ("linear", False, False, 5, 1, 8),                  # more than 4 channels: several 128-bit groups per texel
+    ("linear-mipmap-linear", True, True, 8, 2, 16),
 ]
 
 
