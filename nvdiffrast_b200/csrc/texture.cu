@@ -881,7 +881,8 @@ static __device__ __forceinline__ TexPixelGrad texgrad_group(const TexParams& p,
         // (1-v,1-u) share two of the four weights).  One-value prefilter first: almost every non-uniform group stops there.
         const unsigned full = 0xffffffffu;
         int key0 = act ? (tc0.x ^ (level0 << 27)) : -1 - lane;
-        bool uniform = __all_sync(full, act && !two && key0 == __shfl_sync(full, key0, 0));
+        const int key_l0 = __shfl_sync(full, key0, 0);                  // collectives are evaluated by every lane: never inside a short-circuit
+        bool uniform = __all_sync(full, act && !two && key0 == key_l0);
         if (uniform)
         {
             unsigned d = (unsigned)(__shfl_sync(full, tc0.y, 0) ^ tc0.y) | (unsigned)(__shfl_sync(full, tc0.z, 0) ^ tc0.z) | (unsigned)(__shfl_sync(full, tc0.w, 0) ^ tc0.w);
