@@ -129,6 +129,9 @@ def op_bytes(workload, P, A, D, C):
         "b200dr_antialias_grad": 8 * C * P,
         "b200dr_texture_fwd": (8 + 4 * C + 16) * P,
         "b200dr_texture_grad": (16 + 4 * C + 32) * P,
+        # fused texture -> interpolate -> rasterize backward: dy + rast + rast_db in, nothing per-pixel out (the three ops it
+        # replaces move (16+4C+32) + (32+4A+32+8D) + 48 = 196 B/px through their tensor boundaries)
+        "b200dr_texture_chain_grad": (4 * C + 32) * P,
     }
     return b
 
@@ -359,7 +362,7 @@ def timed_run(pipe, K, W, world, rank, local, device, impl, min_seconds=MIN_TIME
             "trace": trace, "launches": launches}
 
 
-def e2e_run(pipe, K, world, device):
+def e2e_run(pipe, K, world, device, min_seconds=MIN_TIMED_SECONDS):
     """Double-buffered end-to-end loop: step i+1's inputs travel host->device on a copy stream while step i computes; the
     loss and the vertex gradient of step i are read back asynchronously and consumed (event wait) while step i+1 is in
     flight.  All uploads and read-backs happen inside the timed region; rounds of K steps until >= 1 s."""
@@ -404,7 +407,7 @@ def e2e_run(pipe, K, world, device):
         e1.record(); e1.synchronize()
         assert len(losses) == K and all(np.isfinite(l) for l in losses)
         total_ms += e0.elapsed_time(e1); rounds += 1
-        go = torch.tensor([1.0 if (time.perf_counter() - t_start) < MIN_TIMED_SECONDS and rounds < 200 else 0.0], device=device)
+        go = torch.tensor([1.0 if (time.perf_counter() - t_start) < min_seconds and rounds < 200 else 0.0], device=device)
         if world > 1:
             torch.distributed.broadcast(go, 0)
         if float(go.item()) == 0.0:
@@ -499,6 +502,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip other_configs / target_kernels")
+    ap.add_argument("--min-seconds", type=float, default=MIN_TIMED_SECONDS, help="rounds of K steps are repeated until the timed region lasted this long")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -532,14 +536,14 @@ def main():
     P = n_img * res * res
 
     # ---- device-resident timing
-    r = timed_run(pipe, K, W, world, rank, local, device, args.impl)
+    r = timed_run(pipe, K, W, world, rank, local, device, args.impl, args.min_seconds)
     ms_step = r["ms_per_step"]
     value = world * P / (ms_step * 1e-3) / 1e6
 
     # ---- end to end: inputs from pinned host memory every step, loss + vertex gradient read back every step
     e2e = None
     if not args.no_e2e:
-        ms2, rounds2 = e2e_run(pipe, K, world, device)
+        ms2, rounds2 = e2e_run(pipe, K, world, device, args.min_seconds)
         e2e = {"value": world * P / (ms2 * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": ms2, "timed_rounds": rounds2,
                "h2d_bytes_per_step": pipe.h2d_bytes(), "d2h_bytes_per_step": pipe.d2h_bytes()}
 
@@ -585,6 +589,26 @@ def main():
         chain_bytes = sum(nbytes[n] * ops[n][1] / Kt for n in ops if n in nbytes)
         out["chain_roofline"] = {"algorithmic_bytes_per_step": chain_bytes, "achieved_GBps": chain_bytes / (ms_step * 1e-3) / 1e9,
                                  "frac": chain_bytes / (ms_step * 1e-3) / 1e9 / peak}
+        fused = "b200dr_texture_chain_grad" in ops
+        out["fusion"] = {"enabled": bool(mod.get_fusion()), "chain_backward_fused": fused,
+                         "note": "texture+interpolate+rasterize backward run as ONE kernel that keeps g_uv/g_uv_da/g_rast/g_rast_db in registers: "
+                                 "it moves 44 of the 196 B/px the three reference ops move and is bound by instruction issue, not HBM; "
+                                 "`ops_unfused` times the op-by-op path (B200DR_FUSION=0) on the same inputs" if fused else None}
+        if fused:
+            api_bytes = sum(v * ops[n][1] / Kt for n, v in nbytes.items() if n in ops and n != "b200dr_texture_chain_grad") + 196 * P
+            out["chain_roofline"]["op_by_op_bytes_per_step"] = api_bytes
+            out["chain_roofline"]["effective_frac_vs_op_by_op_bytes"] = api_bytes / (ms_step * 1e-3) / 1e9 / peak
+        if fused and world == 1 and not args.no_extras:
+            mod.set_fusion(False)
+            try:
+                ru = timed_run(pipe, K, 1, world, rank, local, device, args.impl, min(args.min_seconds, 0.6))
+            finally:
+                mod.set_fusion(True)
+            tu, opsu = ops_table(ru["trace"], K * ru["rounds"], nbytes, peak)
+            cb = sum(nbytes[n] * opsu[n][1] / (K * ru["rounds"]) for n in opsu if n in nbytes)
+            out["ops_unfused"] = {"ms_per_step": ru["ms_per_step"], "value": P / (ru["ms_per_step"] * 1e-3) / 1e6, "clocks": ru["clocks"],
+                                  "ops": {k: {"ms": v["ms"], "frac": v.get("frac")} for k, v in tu.items()},
+                                  "chain_roofline": {"algorithmic_bytes_per_step": cb, "frac": cb / (ru["ms_per_step"] * 1e-3) / 1e9 / peak}}
         if world == 1 and not args.no_extras and workload == "c3":
             del pipe
             torch.cuda.empty_cache()

@@ -57,10 +57,13 @@ def load():
     elif _build.needs_build():
         try:
             _build.build()
-        except Exception as e:  # no nvcc on this box: fall through to a prebuilt library if there is one
+        except FileNotFoundError as e:  # no nvcc on this box: a prebuilt library (it travels with the tree) is acceptable
             if not os.path.exists(path):
-                raise RuntimeError("nvdiffrast_b200: libb200dr.so is missing and could not be built (%s). "
+                raise RuntimeError("nvdiffrast_b200: libb200dr.so is missing and nvcc is not available (%s). "
                                    "There is no CPU fallback." % e)
+            import warnings
+            warnings.warn("nvdiffrast_b200: sources are newer than libb200dr.so but nvcc is not available; using the prebuilt library")
+        # any other failure (a compile error after a source edit) propagates: never run stale kernels silently
     lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch: fail loudly

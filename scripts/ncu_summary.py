@@ -8,7 +8,7 @@ M = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 
      'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
      'smsp__inst_executed.sum', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed']
 opmap = {"raster_bins_kernel": "rasterize_fwd", "interpolate_fwd_fast": "interpolate_fwd", "texture_fwd_fast": "texture_fwd", "aa_discontinuity_kernel": "antialias_fwd",
-         "aa_copy_kernel": "antialias_grad", "texture_grad_fast": "texture_grad", "interpolate_grad_fast": "interpolate_grad", "raster_grad_kernel": "rasterize_grad"}
+         "aa_copy_kernel": "antialias_grad", "texture_chain_grad_fast": "texture_chain_grad", "texture_grad_fast": "texture_grad", "interpolate_grad_fast": "interpolate_grad", "raster_grad_kernel": "rasterize_grad"}
 lines = ["# ncu --set full, one kernel per capture (c3 workload, 4 images = 16.8 Mpixel per launch, --clock-control none)\n",
          "| kernel | time us | DRAM read MB | DRAM write MB | DRAM B/px | DRAM % | L1 % | L2 % | issue active % | warps active % | regs | warp-inst / 32 px |", "|---|---|---|---|---|---|---|---|---|---|---|---|"]
 traffic = {}
@@ -39,5 +39,5 @@ if os.path.exists(ll):
         lines.append("| %s | %d | %.1f | %.1f |" % (k, c, t / 1e3, 100 * t / tot))
     import shutil; shutil.copy(ll, os.path.join(dst, "%s_launches_c3.csv" % tag))
 open(os.path.join(dst, "%s_ncu_kernels.md" % tag), "w").write("\n".join(lines) + "\n")
-json.dump(traffic, open(os.path.join(dst, "r01_traffic.json"), "w"), indent=1)
+json.dump(traffic, open(os.path.join(dst, "%s_traffic.json" % tag), "w"), indent=1)
 print("\n".join(lines))
