@@ -341,17 +341,22 @@ static __device__ __forceinline__ void red_add2(float* p, float2 v)
     asm volatile("red.global.v2.f32.add [%0], {%1,%2};" :: "l"(p), "f"(v.x), "f"(v.y) : "memory");
 }
 
-// ---- L2 prefetch of a contiguous byte range (UBLKPF.L2: no registers, no shared memory, no completion to wait for).
-// Streaming kernels walk their per-pixel tensors with a fixed grid stride, so a warp knows the addresses of its NEXT group
-// while it works on the current one: one elected lane asks L2 to fetch them, and the later demand loads find the lines in
-// L2 (~1/3 of the DRAM latency) instead of stalling the warp on HBM.  addr 16-byte aligned, bytes a multiple of 16.
+// ---- L2 prefetch of a warp's NEXT pixel group (streaming kernels walk their tensors with a fixed grid stride, so the
+// addresses are known one iteration ahead).  Measured on c3 (profiles/r02_experiments.md): the bulk form (UBLKPF.L2, one
+// elected lane, goes through the TMA unit) SLOWS the texture kernels by 3-26 % at two to three 256-512 byte requests per
+// group and gains 1-2 % elsewhere; it is therefore off by default.  DR_PREFETCH = 1: bulk form; 2: one
+// prefetch.global.L2 per lane (LSU path, 16 bytes apart).  All lanes call; addr 16-byte aligned, bytes <= 512, multiple of 16.
 #ifndef DR_PREFETCH
-#define DR_PREFETCH 1
+#define DR_PREFETCH 0
 #endif
-static __device__ __forceinline__ void prefetch_l2(const void* addr, uint32_t bytes)
+static __device__ __forceinline__ void warp_prefetch_l2(const void* addr, uint32_t bytes, int lane)
 {
-#if DR_PREFETCH
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(addr), "r"(bytes) : "memory");
+#if DR_PREFETCH == 1
+    if (lane == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(addr), "r"(bytes) : "memory");
+#elif DR_PREFETCH == 2
+    if ((uint32_t)lane * 16u < bytes) asm volatile("prefetch.global.L2 [%0];" :: "l"((const char*)addr + lane * 16) : "memory");
+#else
+    (void)addr; (void)bytes; (void)lane;
 #endif
 }
 

@@ -299,15 +299,14 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_fwd_fast(const InterpP
             r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (inb[u]) r[u] = ld_stream_f4((const float4*)p.rast + img + px);
         }
-        if (lane == 0)                                  // this warp's next groups: ask L2 for their rast lines now
+#if DR_PREFETCH
+        #pragma unroll
+        for (int u = 0; u < IPF_UNROLL; u++)
         {
-            #pragma unroll
-            for (int u = 0; u < IPF_UNROLL; u++)
-            {
-                const int gn = g0 + (IPF_UNROLL + u) * wstride;
-                if (gn * 32 + 32 <= hw) prefetch_l2((const float4*)p.rast + img + (size_t)gn * 32, 512);
-            }
+            const int gn = g0 + (IPF_UNROLL + u) * wstride;
+            if (gn * 32 + 32 <= hw) warp_prefetch_l2((const float4*)p.rast + img + (size_t)gn * 32, 512, lane);
         }
+#endif
         #pragma unroll
         for (int u = 0; u < IPF_UNROLL; u++)
         {
@@ -397,16 +396,15 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const Interp
             r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (inb[u]) r[u] = ld_stream_f4((const float4*)p.rast + img + px);
         }
-        if (lane == 0)                                  // this warp's next groups: ask L2 for their lines now
+#if DR_PREFETCH
+        #pragma unroll
+        for (int u = 0; u < IPF_UNROLL; u++)
         {
-            #pragma unroll
-            for (int u = 0; u < IPF_UNROLL; u++)
-            {
-                const int gn = g0 + (IPF_UNROLL + u) * wstride;
-                // only rast: dy / dda / rast_db are fetched under geometry only, prefetching them would add the bytes back
-                if (gn * 32 + 32 <= hw) prefetch_l2((const float4*)p.rast + img + (size_t)gn * 32, 512);
-            }
+            const int gn = g0 + (IPF_UNROLL + u) * wstride;
+            // only rast: dy / dda / rast_db are fetched under geometry only, prefetching them would add the bytes back
+            if (gn * 32 + 32 <= hw) warp_prefetch_l2((const float4*)p.rast + img + (size_t)gn * 32, 512, lane);
         }
+#endif
         #pragma unroll
         for (int u = 0; u < IPF_UNROLL; u++)
         {

@@ -830,9 +830,12 @@ static __device__ __forceinline__ void raster_grad_pixel(const RastGradParams& p
     for (int m = 0; m < 3; m++) { g[3 * m] = gx[m]; g[3 * m + 1] = gy[m]; g[3 * m + 2] = gw[m]; }
 }
 
-// Shared-memory gradient accumulators pay a CAS loop per fp32 add; they win only while few vertices make global reductions collide.
-#ifndef ACC_SMEM_MAX_V
-#define ACC_SMEM_MAX_V (1 << 30)
+// Shared-memory gradient accumulators pay a compare-and-swap loop per fp32 add (ATOMS.CAST.SPIN; only 32-bit integer adds are
+// native in shared memory): they win only while so few vertices exist that global reductions would collide (c2: 8 vertices).
+// Above the threshold every triangle run issues one 128-bit global vector reduction per vertex instead (measured on c3,
+// 2 930 vertices x 16 images: 0.724 -> 0.664 ms).
+#ifndef RG_SMEM_MAX_V
+#define RG_SMEM_MAX_V 1024
 #endif
 #ifndef RG_UNROLL
 #define RG_UNROLL 2
@@ -871,15 +874,14 @@ __global__ void __launch_bounds__(256, RG_MINB) raster_grad_kernel(const RastGra
             ro[u] = make_float4(0.f, 0.f, 0.f, 0.f); ddb[u] = ro[u]; dy[u] = make_float2(0.f, 0.f);
             if (inb[u]) ro[u] = ld_stream_f4((const float4*)p.rast + img + r);
         }
-        if (lane == 0)                                  // this warp's next groups: ask L2 for their rast lines now
+#if DR_PREFETCH
+        #pragma unroll
+        for (int u = 0; u < RG_UNROLL; u++)
         {
-            #pragma unroll
-            for (int u = 0; u < RG_UNROLL; u++)
-            {
-                const int gn = g0 + (RG_UNROLL + u) * wstride;
-                if (gn * 32 + 32 <= hw) prefetch_l2((const float4*)p.rast + img + (size_t)gn * 32, 512);
-            }
+            const int gn = g0 + (RG_UNROLL + u) * wstride;
+            if (gn * 32 + 32 <= hw) warp_prefetch_l2((const float4*)p.rast + img + (size_t)gn * 32, 512, lane);
         }
+#endif
         // incoming gradients are fetched only under geometry (empty pixels cost 16 instead of 40-48 bytes); the extra
         // dependency runs in parallel with the triangle -> vertex gathers
         #pragma unroll
@@ -1098,7 +1100,7 @@ extern "C" int b200dr_rasterize_grad(const float* pos, const int32_t* tri, const
     size_t hw = (size_t)H * W;
     p.chunks = (int)((hw + 255) / 256);
     size_t smem = (size_t)V * 4 * sizeof(float);
-    p.use_smem = (smem <= 64 * 1024 && V <= ACC_SMEM_MAX_V) ? 1 : 0;
+    p.use_smem = (smem <= 64 * 1024 && V <= RG_SMEM_MAX_V) ? 1 : 0;
     // Persistent-ish grid: enough CTAs to fill the machine, few enough that the shared-memory flush stays negligible.
     int target = b200dr_num_sms() * RG_MINB;
     int gx = p.use_smem ? max(target / N, 1) : 16384;       // shared accumulators: one resident wave, rounded down

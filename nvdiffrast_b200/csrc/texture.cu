@@ -563,7 +563,7 @@ static __device__ __forceinline__ void uni_store_key(UniKey* slot, float2 uv, fl
 // experiment, off by default, needs W % 8 == 0 and H % 4 == 0): an 8x4 pixel tile, so that neighbouring lanes share texel
 // quads in both directions (fewer distinct sectors per tap instruction, longer merge runs).
 #ifndef TEXG_TILE2D
-#define TEXG_TILE2D 0
+#define TEXG_TILE2D 1
 #endif
 static __device__ __forceinline__ size_t group_pixel(const TexParams& p, size_t g, int lane)
 {
@@ -636,19 +636,18 @@ __global__ void __launch_bounds__(TEX_THREADS, TEXF_MINB) texture_fwd_fast(const
                 if (mip && m.has_bias) bias[u] = ld_stream_f(p.bias + pidx);
             }
         }
-        if (lane == 0 && !p.tile2d)                     // this warp's next groups: ask L2 for their lines now
+#if DR_PREFETCH
+        #pragma unroll
+        for (int u = 0; u < TEXF_UNROLL; u++)
         {
-            #pragma unroll
-            for (int u = 0; u < TEXF_UNROLL; u++)
+            const size_t gn = g0 + (TEXF_UNROLL + u) * wstride;
+            if (gn * 32 + 32 <= total)
             {
-                const size_t gn = g0 + (TEXF_UNROLL + u) * wstride;
-                if (gn * 32 + 32 <= total)
-                {
-                    prefetch_l2(p.uv + gn * 64, 256);
-                    if (mip && m.has_da) prefetch_l2(p.uv_da + gn * 128, 512);
-                }
+                warp_prefetch_l2(p.uv + gn * 64, 256, lane);
+                if (mip && m.has_da) warp_prefetch_l2(p.uv_da + gn * 128, 512, lane);
             }
         }
+#endif
         #pragma unroll
         for (int u = 0; u < TEXF_UNROLL; u++)
         {
@@ -1027,7 +1026,8 @@ __global__ void __launch_bounds__(TEXG_THREADS, TEXG_MINB) texture_grad_fast(con
         TexGradIn<C> in[TEXG_UNROLL];
         #pragma unroll
         for (int u = 0; u < TEXG_UNROLL; u++) texgrad_issue<C>(p, m, g0 + u * wstride, groups, total, lane, in[u]);
-        if (lane == 0 && !p.tile2d)                     // this warp's next groups: ask L2 for their lines now
+#if DR_PREFETCH
+        if (!p.tile2d)
         {
             #pragma unroll
             for (int u = 0; u < TEXG_UNROLL; u++)
@@ -1035,12 +1035,13 @@ __global__ void __launch_bounds__(TEXG_THREADS, TEXG_MINB) texture_grad_fast(con
                 const size_t gn = g0 + (TEXG_UNROLL + u) * wstride;
                 if (gn * 32 + 32 <= total)
                 {
-                    prefetch_l2(p.dy + gn * 32 * C, 32 * C * 4);
-                    prefetch_l2(p.uv + gn * 64, 256);
-                    if (m.has_da) prefetch_l2(p.uv_da + gn * 128, 512);
+                    warp_prefetch_l2(p.dy + gn * 32 * C, 32 * C * 4, lane);
+                    warp_prefetch_l2(p.uv + gn * 64, 256, lane);
+                    if (m.has_da) warp_prefetch_l2(p.uv_da + gn * 128, 512, lane);
                 }
             }
         }
+#endif
         #pragma unroll
         for (int u = 0; u < TEXG_UNROLL; u++)
             if (in[u].g < groups) texgrad_group<C, B, true>(p, m, in[u], pd, cached, &s_slot[warp], lane, s_stage[warp], hw, trilinear);   // warp-uniform
@@ -1125,11 +1126,12 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
         if (in.inb) r = ld_stream_f4((const float4*)q.rast + pidx);
         warp_load_aos_issue<C>(p.dy + g * 32 * C, in.dy, lane, in.inb, in.full);
-        if (lane == 0)                                  // this warp's next group: ask L2 for its rast and dy lines now
+#if DR_PREFETCH
         {
             const size_t gn = g + wstride;
-            if (gn * 32 + 32 <= total) { prefetch_l2((const float4*)q.rast + gn * 32, 512); prefetch_l2(p.dy + gn * 32 * C, 32 * C * 4); }
+            if (gn * 32 + 32 <= total) { warp_prefetch_l2((const float4*)q.rast + gn * 32, 512, lane); warp_prefetch_l2(p.dy + gn * 32 * C, 32 * C * 4, lane); }
         }
+#endif
 
         // ---- triangle of the pixel, attribute rows, recomputed texture coordinates
         const int n = (int)(pidx / hw);

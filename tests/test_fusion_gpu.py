@@ -1,6 +1,6 @@
 """Fused chain backward (texture -> interpolate -> rasterize in one kernel, nvdiffrast_b200/torch/ops.py `_fusion_plan`):
 same results as the op-by-op path, engaged only when the provenance of uv / uv_da / rast / rast_db is proven, and summed
-correctly with every other gradient path.  Tolerance: forward bitwise identical (same kernel); accumulated gradients
+correctly with every other gradient path.  Tolerance: forward 1e-6 (same kernels; antialias' atomic blend order varies); accumulated gradients
 |d|_inf <= 2e-5 |g|_inf (only the summation order differs); per-pixel gradients abs 1e-6 |g|_inf + rel 1e-5."""
 import numpy as np
 import pytest
@@ -96,7 +96,8 @@ def _compare(dr, ctx, c, n, expect_fused=True, expect_raster_fused=True, **kw):
         assert "texture_grad" not in ops_f
         if expect_raster_fused and not kw.get("extra_uv_loss"):
             assert "interpolate_grad" not in ops_f and "rasterize_grad" not in ops_f, ops_f
-    assert torch.equal(out_f, out_u)
+    # the forward kernels are the same in both modes; antialias blends with fp32 atomics whose order varies from run to run
+    assert float((out_f - out_u).abs().max()) <= 1e-6
     assert set(g_f) == set(g_u) and len(g_u) > 0
     for k in g_u:
         d = float((g_f[k].double() - g_u[k].double()).abs().max()); sc = float(g_u[k].abs().max())

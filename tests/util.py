@@ -102,15 +102,17 @@ EPS32 = 2.0 ** -24
 
 
 def raster_condition(pos, tri, rast, res):
-    """Condition number of the barycentrics of every covered pixel, from a float64 evaluation of the edge functions:
-    cond = sum_i (|qx_j qy_k| + |qy_j qx_k|) / |sum_i e_i|.  u, v = e_i / sum(e) carry a rounding error of a few
-    2^-24 * cond whatever the operation order (sliver and sub-pixel triangles have a tiny sum(e) made of O(1) products).
-    Returns (cond [N,H,W], covered mask)."""
+    """Condition numbers of the shaded values of every covered pixel, from a float64 evaluation of the edge functions.
+      barycentrics: u, v = e_i / sum(e); each e_i = q_j x q_k carries an absolute rounding error of about 2^-24 m_i with
+                    m_i = |qx_j qy_k| + |qy_j qx_k|, whatever the operation order -> cond_uv = sum(m) / |sum(e)|
+                    (sliver and sub-pixel triangles have a tiny sum(e) made of O(1) products);
+      depth:        z/w = sum(z_i e_i) / sum(w_i e_i) -> cond_zw = (sum |z_i| m_i + |z/w| sum |w_i| m_i) / |sum(w_i e_i)|.
+    Returns (cond [N,H,W,3] for the (u, v, z/w) channels, covered mask)."""
     pos = np.asarray(pos, np.float64); tri = np.asarray(tri)
     H, W = res
     ids = np.asarray(rast)[..., 3].astype(np.int64)
     N = ids.shape[0]
-    cond = np.zeros(ids.shape, np.float64)
+    cond = np.zeros(ids.shape + (3,), np.float64)
     fx = (2.0 / W) * np.arange(W) + (1.0 / W - 1.0)
     fy = (2.0 / H) * np.arange(H) + (1.0 / H - 1.0)
     for n in range(N):
@@ -119,22 +121,29 @@ def raster_condition(pos, tri, rast, res):
         vb = pos[n] if pos.ndim == 3 else pos
         p = vb[t]                                               # [K,3,4]
         qx = p[:, :, 0] - fx[xs, None] * p[:, :, 3]; qy = p[:, :, 1] - fy[ys, None] * p[:, :, 3]
-        num = np.zeros(len(ys)); den = np.zeros(len(ys))
+        m = np.zeros((len(ys), 3)); e = np.zeros((len(ys), 3))
         for i in range(3):
             j, k = (i + 1) % 3, (i + 2) % 3
-            num += np.abs(qx[:, j] * qy[:, k]) + np.abs(qy[:, j] * qx[:, k])
-            den += qx[:, j] * qy[:, k] - qy[:, j] * qx[:, k]
-        cond[n, ys, xs] = num / np.maximum(np.abs(den), 1e-300)
+            m[:, i] = np.abs(qx[:, j] * qy[:, k]) + np.abs(qy[:, j] * qx[:, k])
+            e[:, i] = qx[:, j] * qy[:, k] - qy[:, j] * qx[:, k]
+        S = np.maximum(np.abs(e.sum(1)), 1e-300)
+        wn = (p[:, :, 3] * e).sum(1); zn = (p[:, :, 2] * e).sum(1)
+        awn = np.maximum(np.abs(wn), 1e-300)
+        zw = np.clip(zn / np.where(wn == 0, 1e-300, wn), -1.0, 1.0)
+        cuv = m.sum(1) / S
+        czw = ((np.abs(p[:, :, 2]) * m).sum(1) + np.abs(zw) * (np.abs(p[:, :, 3]) * m).sum(1)) / awn
+        cond[n, ys, xs, 0] = cuv; cond[n, ys, xs, 1] = cuv; cond[n, ys, xs, 2] = czw
     return cond, ids > 0
 
 
 def assert_close_cond(a, b, cond, atol, rtol, k, name=""):
-    """|a - b| <= atol + rtol |b| + k 2^-24 cond  for every element (cond broadcast over the channel axis)."""
+    """|a - b| <= atol + rtol |b| + k 2^-24 cond  for every element (cond per element, or per pixel and broadcast)."""
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
-    tol = atol + rtol * np.abs(b) + k * EPS32 * cond[..., None]
+    c = cond if cond.ndim == a.ndim else cond[..., None]
+    tol = atol + rtol * np.abs(b) + k * EPS32 * c
     bad = np.abs(a - b) > tol
     assert not bad.any(), "%s: %d elements outside atol=%g rtol=%g k=%g (worst excess %.3g at cond %.3g)" % (
-        name, int(bad.sum()), atol, rtol, k, float((np.abs(a - b) - tol).max()), float(cond[bad.any(-1)].max()))
+        name, int(bad.sum()), atol, rtol, k, float((np.abs(a - b) - tol).max()), float(np.broadcast_to(c, a.shape)[bad].max()))
 
 
 def mip_level_f64(uv_da, bias, tex_w, tex_h, max_level):
