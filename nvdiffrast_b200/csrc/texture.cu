@@ -565,10 +565,11 @@ static __device__ __forceinline__ void uni_store_key(UniKey* slot, float2 uv, fl
 #ifndef TEXG_TILE2D
 #define TEXG_TILE2D 1
 #endif
+template <bool TILE>
 static __device__ __forceinline__ size_t group_pixel(const TexParams& p, size_t g, int lane)
 {
 #if TEXG_TILE2D
-    if (p.tile2d)
+    if (TILE && p.tile2d)
     {
         unsigned t = (unsigned)g, n = t / (unsigned)p.tilesPerImg, r = t - n * (unsigned)p.tilesPerImg;
         unsigned ty = r / (unsigned)p.tilesX, tx = r - ty * (unsigned)p.tilesX;
@@ -589,17 +590,7 @@ static __device__ __forceinline__ size_t group_pixel(const TexParams& p, size_t 
 template <int C>
 static __device__ __forceinline__ void tex_store_out(const TexParams& p, size_t g, size_t pidx, const float (&o)[C], int lane, bool inb, bool full, float* stage)
 {
-#if TEXG_TILE2D
-    if (p.tile2d)
-    {
-        if (inb)
-        {
-            #pragma unroll
-            for (int i = 0; i < C; i++) p.out[pidx * C + i] = o[i];
-        }
-        return;
-    }
-#endif
+    (void)pidx;
     warp_store_aos<C>(p.out + g * 32 * C, o, lane, inb, full, stage);
 }
 
@@ -626,7 +617,7 @@ __global__ void __launch_bounds__(TEX_THREADS, TEXF_MINB) texture_fwd_fast(const
         #pragma unroll
         for (int u = 0; u < TEXF_UNROLL; u++)
         {
-            size_t pidx = group_pixel(p, g0 + u * wstride, lane);
+            size_t pidx = group_pixel<false>(p, g0 + u * wstride, lane);
             inb[u] = (g0 + u * wstride < groups) && (pidx < total);
             uv[u] = make_float2(0.f, 0.f); da[u] = make_float4(0.f, 0.f, 0.f, 0.f); bias[u] = 0.f;
             if (inb[u])
@@ -653,7 +644,7 @@ __global__ void __launch_bounds__(TEX_THREADS, TEXF_MINB) texture_fwd_fast(const
         {
             size_t g = g0 + u * wstride;
             if (g >= groups) continue;                  // warp-uniform
-            size_t pidx = group_pixel(p, g, lane);
+            size_t pidx = group_pixel<false>(p, g, lane);
             const bool full = (g * 32 + 32 <= total);
             const int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
             float o[C];
@@ -765,7 +756,7 @@ template <int C>
 static __device__ __forceinline__ void texgrad_issue(const TexParams& p, const TexMode& m, size_t g, size_t groups, size_t total, int lane, TexGradIn<C>& in)
 {
     in.g = g;
-    size_t pidx = group_pixel(p, g, lane);
+    size_t pidx = group_pixel<true>(p, g, lane);
     in.pidx = pidx;
     in.inb = (g < groups) && (pidx < total);
     in.full = (g < groups) && (g * 32 + 32 <= total);
@@ -1094,7 +1085,7 @@ static __device__ __forceinline__ void interp_uv(float4 r, float4 db, const floa
 }
 
 #ifndef TCG_MINB
-#define TCG_MINB 4
+#define TCG_MINB 5          // <= 102 registers: 20 warps per SM (measured 2.72 -> 2.39 ms against 4 CTAs at 118 registers; 3 CTAs: 2.82)
 #endif
 
 template <int C, int F, int B, bool RASTER>
@@ -1116,7 +1107,12 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
     for (int i = 0; i < C; i++) pd.sum[i] = 0.f;
     bool cached = false;
 
-    for (size_t g = (size_t)blockIdx.x * (TEXG_THREADS / 32) + warp; g < groups; g += wstride)
+    // image / in-image offset of the warp's current group, advanced incrementally (no 64-bit division per pixel); hw < 2^30
+    size_t g = (size_t)blockIdx.x * (TEXG_THREADS / 32) + warp;
+    int n0 = (int)((g * 32) / hw);
+    unsigned r0 = (unsigned)(g * 32 - (size_t)n0 * hw);
+    const unsigned hw32 = (unsigned)hw;
+    for (; g < groups; g += wstride)
     {
         TexGradIn<C> in;
         in.g = g; in.pidx = g * 32 + lane;
@@ -1126,21 +1122,35 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
         if (in.inb) r = ld_stream_f4((const float4*)q.rast + pidx);
         warp_load_aos_issue<C>(p.dy + g * 32 * C, in.dy, lane, in.inb, in.full);
-#if DR_PREFETCH
-        {
+        {   // this warp's next group: one prefetch.global.L2 per lane and tensor (LSU path; measured -5 % on this kernel, whose
+            // iterations are long enough for the lines to arrive; the bulk / TMA form and the short-iteration kernels lose)
             const size_t gn = g + wstride;
-            if (gn * 32 + 32 <= total) { warp_prefetch_l2((const float4*)q.rast + gn * 32, 512, lane); warp_prefetch_l2(p.dy + gn * 32 * C, 32 * C * 4, lane); }
+            if (gn * 32 + 32 <= total)
+            {
+                asm volatile("prefetch.global.L2 [%0];" :: "l"((const float4*)q.rast + gn * 32 + lane) : "memory");
+                if (lane * 16 < 32 * C * 4) asm volatile("prefetch.global.L2 [%0];" :: "l"((const char*)(p.dy + gn * 32 * C) + lane * 16) : "memory");
+            }
         }
-#endif
 
         // ---- triangle of the pixel, attribute rows, recomputed texture coordinates
-        const int n = (int)(pidx / hw);
+        unsigned rl = r0 + (unsigned)lane;              // pixel index inside image n
+        int n = n0;
+        if (rl >= hw32) { rl -= hw32; n++; }
+        {   // advance the warp's (image, offset) to its next group
+            size_t adv = (size_t)r0 + wstride * 32;
+            while (adv >= hw) { adv -= hw; n0++; }
+            r0 = (unsigned)adv;
+        }
         int triIdx = in.inb ? float_to_triidx(r.w) - 1 : -1;
         if (triIdx >= q.T) triIdx = -1;
-        int ai0 = 0, ai1 = 0, ai2 = 0;
+        int ai0 = 0, ai1 = 0, ai2 = 0, vi0 = 0, vi1 = 0, vi2 = 0;
         if (triIdx >= 0)
         {
             ai0 = __ldg(q.attr_tri + triIdx * 3); ai1 = __ldg(q.attr_tri + triIdx * 3 + 1); ai2 = __ldg(q.attr_tri + triIdx * 3 + 2);
+            if (RASTER && q.g_pos)                      // position indices are fetched with the attribute indices: one round trip
+            {
+                vi0 = __ldg(q.pos_tri + triIdx * 3); vi1 = __ldg(q.pos_tri + triIdx * 3 + 1); vi2 = __ldg(q.pos_tri + triIdx * 3 + 2);
+            }
             if (ai0 < 0 || ai0 >= q.Va || ai1 < 0 || ai1 >= q.Va || ai2 < 0 || ai2 >= q.Va) triIdx = -1;
         }
         const bool valid = triIdx >= 0;
@@ -1219,13 +1229,8 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
             float gv9[9];
             #pragma unroll
             for (int i = 0; i < 9; i++) gv9[i] = 0.f;
-            int vi0 = 0, vi1 = 0, vi2 = 0;
             bool pv = valid;
-            if (pv)
-            {
-                vi0 = __ldg(q.pos_tri + triIdx * 3); vi1 = __ldg(q.pos_tri + triIdx * 3 + 1); vi2 = __ldg(q.pos_tri + triIdx * 3 + 2);
-                if (vi0 < 0 || vi0 >= q.V || vi1 < 0 || vi1 >= q.V || vi2 < 0 || vi2 >= q.V) pv = false;
-            }
+            if (pv && (vi0 < 0 || vi0 >= q.V || vi1 < 0 || vi1 >= q.V || vi2 < 0 || vi2 >= q.V)) pv = false;
             // the reference skips pixels whose incoming gradients are all +-0 (csrc/common/rasterize.cu:143-148)
             const unsigned nz_dy = (__float_as_uint(gr.x) | __float_as_uint(gr.y)) << 1;
             const unsigned nz_db = q.grad_db ? ((__float_as_uint(gdb.x) | __float_as_uint(gdb.y) | __float_as_uint(gdb.z) | __float_as_uint(gdb.w)) << 1) : 0u;
@@ -1233,8 +1238,7 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
             if (pv)
             {
                 const float4* vb = (const float4*)q.pos + (size_t)n * q.V;
-                const int rp = (int)(pidx - (size_t)n * hw);
-                const int py = rp / p.W, px = rp - py * p.W;
+                const unsigned py = rl / (unsigned)p.W, px = rl - py * (unsigned)p.W;
                 const float fx = q.xs * (float)px + q.xo, fy = q.ys * (float)py + q.yo;
                 pm::PixelTri t;
                 pm::pixel_tri(t, __ldg(vb + vi0), __ldg(vb + vi1), __ldg(vb + vi2), fx, fy);
@@ -2113,6 +2117,7 @@ extern "C" int b200dr_texture_chain_grad(const float* tex, const float* const* m
     const bool mip = (filter_mode != B200DR_FILTER_LINEAR);
     B200DR_CHECK(!mip || rast_db, "%s: mipmapped filtering needs rast_db (pixel differentials of the attributes)", fn);
     B200DR_CHECK(attr && attr_tri && rast && dy && Va > 0 && T > 0, "%s: missing input", fn);
+    B200DR_CHECK((size_t)H * W < (1u << 30), "%s: image too large", fn);
     B200DR_CHECK(B200DR_ALIGNED16(rast) && B200DR_ALIGNED16(rast_db) && B200DR_ALIGNED16(dy) && (((uintptr_t)attr) & 7) == 0, "%s: input tensor misaligned", fn);
     B200DR_CHECK(!pos || (pos_tri && V > 0 && B200DR_ALIGNED16(pos)), "%s: pos / tri missing or misaligned", fn);
     B200DR_CHECK(B200DR_ALIGNED16(g_rast) && B200DR_ALIGNED16(g_rast_db) && (!g_rast || g_rast_db || !rast_db), "%s: g_rast outputs missing or misaligned", fn);

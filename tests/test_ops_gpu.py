@@ -77,13 +77,14 @@ def run_rasterize(dr, ctx, pos, tri, res, path=0, ranges=None):
 
 
 def _check_raster_vs_oracle(pos, tri, res, rast, db, o, name):
-    """u, v, z/w and rast_db against the uncontracted CPU oracle, every covered pixel, condition-scaled (no outlier budget)."""
-    cond, covered = raster_condition(pos, tri, o["rast"], res)
+    """u, v, z/w and rast_db against the uncontracted CPU oracle, every covered pixel, tolerance scaled by the pixel's
+    condition number (util.raster_condition; no outlier budget).  The comparison with the reference itself is bitwise
+    (test_rasterize_vs_reference)."""
+    cond, cond_db, covered = raster_condition(pos, tri, o["rast"], res)
     assert np.array_equal(rast[~covered], np.zeros_like(rast[~covered])) and np.array_equal(db[~covered], np.zeros_like(db[~covered]))
-    assert_close_cond(rast[..., :3], o["rast"][..., :3], cond, 1e-6, 1e-5, 16, name + " uvz")
-    # rast_db = (2/W) * (u * sum(n) - n_0) / sum(e): same cancellation, scaled by the derivative's own magnitude
-    scale = cond[..., 0] * np.maximum(np.abs(o["rast_db"]).max(-1), 1e-3)
-    assert_close_cond(db, o["rast_db"], scale, 1e-6, 1e-4, 64, name + " db")
+    # k = 4: two independent fp32 evaluations (the oracle itself is within k = 1 of a float64 evaluation on every scene)
+    assert_close_cond(rast[..., :3], o["rast"][..., :3], cond, 1e-6, 1e-5, 4, name + " uvz")
+    assert_close_cond(db, o["rast_db"], cond_db, 1e-6, 1e-5, 4, name + " db")
 
 
 @pytest.mark.parametrize("name", sorted(SCENES))

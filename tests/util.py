@@ -102,17 +102,23 @@ EPS32 = 2.0 ** -24
 
 
 def raster_condition(pos, tri, rast, res):
-    """Condition numbers of the shaded values of every covered pixel, from a float64 evaluation of the edge functions.
-      barycentrics: u, v = e_i / sum(e); each e_i = q_j x q_k carries an absolute rounding error of about 2^-24 m_i with
-                    m_i = |qx_j qy_k| + |qy_j qx_k|, whatever the operation order -> cond_uv = sum(m) / |sum(e)|
-                    (sliver and sub-pixel triangles have a tiny sum(e) made of O(1) products);
-      depth:        z/w = sum(z_i e_i) / sum(w_i e_i) -> cond_zw = (sum |z_i| m_i + |z/w| sum |w_i| m_i) / |sum(w_i e_i)|.
-    Returns (cond [N,H,W,3] for the (u, v, z/w) channels, covered mask)."""
+    """Condition numbers of the shaded values of every covered pixel, from a float64 evaluation of the edge functions
+    (units of 2^-24: multiply by a small constant k for the tolerance).
+      barycentrics: u, v = e_i / sum(e); each e_i = q_j x q_k carries an absolute rounding error of about 2^-24 m_i, whatever
+                    the operation order, with m_i = |qx_j qy_k| + |qy_j qx_k| + (rounding of q = x - fx w, which cancels O(1)
+                    clip coordinates down to a few pixel widths) -> cond_uv = sum(m) / |sum(e)|: small and sliver triangles
+                    have u, v accurate to 1e-5..1e-4 only, in ANY fp32 evaluation of the reference formula;
+      depth:        z/w = sum(z_i e_i) / sum(w_i e_i) -> cond_zw = (sum |z_i| m_i + |z/w| sum |w_i| m_i) / |sum(w_i e_i)|;
+      rast_db:      d = k (u sn - n_0) with k = (2/W) / sum(e), n_i = y_k w_j - y_j w_k (error 2^-24 mn_i):
+                    cond_db = |k| (cond_uv |sn| + |u| sum(mn) + mn_0 + |u sn| + |n_0|) + cond_uv |d|   (same in y and for v).
+    Returns (cond [N,H,W,3] for (u, v, z/w), cond_db [N,H,W,4], covered mask)."""
     pos = np.asarray(pos, np.float64); tri = np.asarray(tri)
     H, W = res
-    ids = np.asarray(rast)[..., 3].astype(np.int64)
+    rast = np.asarray(rast, np.float64)
+    ids = rast[..., 3].astype(np.int64)
     N = ids.shape[0]
     cond = np.zeros(ids.shape + (3,), np.float64)
+    cond_db = np.zeros(ids.shape + (4,), np.float64)
     fx = (2.0 / W) * np.arange(W) + (1.0 / W - 1.0)
     fy = (2.0 / H) * np.arange(H) + (1.0 / H - 1.0)
     for n in range(N):
@@ -120,20 +126,35 @@ def raster_condition(pos, tri, rast, res):
         t = tri[ids[n, ys, xs] - 1]
         vb = pos[n] if pos.ndim == 3 else pos
         p = vb[t]                                               # [K,3,4]
-        qx = p[:, :, 0] - fx[xs, None] * p[:, :, 3]; qy = p[:, :, 1] - fy[ys, None] * p[:, :, 3]
-        m = np.zeros((len(ys), 3)); e = np.zeros((len(ys), 3))
+        X, Y, Z, Wc = p[:, :, 0], p[:, :, 1], p[:, :, 2], p[:, :, 3]
+        qx = X - fx[xs, None] * Wc; qy = Y - fy[ys, None] * Wc
+        dqx = np.abs(X) + np.abs(fx[xs, None] * Wc); dqy = np.abs(Y) + np.abs(fy[ys, None] * Wc)
+        K = len(ys)
+        m = np.zeros((K, 3)); e = np.zeros((K, 3)); nx = np.zeros((K, 3)); ny = np.zeros((K, 3)); mnx = np.zeros((K, 3)); mny = np.zeros((K, 3))
         for i in range(3):
             j, k = (i + 1) % 3, (i + 2) % 3
-            m[:, i] = np.abs(qx[:, j] * qy[:, k]) + np.abs(qy[:, j] * qx[:, k])
+            # rounding of the products, plus the rounding of q itself: q = x - fx w cancels O(1) clip coordinates down to a few
+            # pixel widths, so its absolute error 2^-24 (|x| + |fx w|) is LARGE relative to q (this term dominates)
+            m[:, i] = (np.abs(qx[:, j] * qy[:, k]) + np.abs(qy[:, j] * qx[:, k])
+                       + dqx[:, j] * np.abs(qy[:, k]) + np.abs(qx[:, j]) * dqy[:, k] + dqy[:, j] * np.abs(qx[:, k]) + np.abs(qy[:, j]) * dqx[:, k])
             e[:, i] = qx[:, j] * qy[:, k] - qy[:, j] * qx[:, k]
+            nx[:, i] = Y[:, k] * Wc[:, j] - Y[:, j] * Wc[:, k]; mnx[:, i] = np.abs(Y[:, k] * Wc[:, j]) + np.abs(Y[:, j] * Wc[:, k])
+            ny[:, i] = X[:, j] * Wc[:, k] - X[:, k] * Wc[:, j]; mny[:, i] = np.abs(X[:, j] * Wc[:, k]) + np.abs(X[:, k] * Wc[:, j])
         S = np.maximum(np.abs(e.sum(1)), 1e-300)
-        wn = (p[:, :, 3] * e).sum(1); zn = (p[:, :, 2] * e).sum(1)
+        wn = (Wc * e).sum(1); zn = (Z * e).sum(1)
         awn = np.maximum(np.abs(wn), 1e-300)
         zw = np.clip(zn / np.where(wn == 0, 1e-300, wn), -1.0, 1.0)
         cuv = m.sum(1) / S
-        czw = ((np.abs(p[:, :, 2]) * m).sum(1) + np.abs(zw) * (np.abs(p[:, :, 3]) * m).sum(1)) / awn
+        czw = ((np.abs(Z) * m).sum(1) + np.abs(zw) * (np.abs(Wc) * m).sum(1)) / awn
         cond[n, ys, xs, 0] = cuv; cond[n, ys, xs, 1] = cuv; cond[n, ys, xs, 2] = czw
-    return cond, ids > 0
+        uvv = rast[n, ys, xs, :2]
+        for c, (nn, mn, sc) in enumerate(((nx, mnx, 2.0 / W), (ny, mny, 2.0 / H))):
+            kk = sc / S
+            sn = nn.sum(1)
+            for b in range(2):                                  # b = 0: u (vertex 0), b = 1: v (vertex 1)
+                d = kk * np.abs(uvv[:, b] * sn - nn[:, b])
+                cond_db[n, ys, xs, 2 * b + c] = kk * (cuv * np.abs(sn) + np.abs(uvv[:, b]) * mn.sum(1) + mn[:, b] + np.abs(uvv[:, b] * sn) + np.abs(nn[:, b])) + cuv * d
+    return cond, cond_db, ids > 0
 
 
 def assert_close_cond(a, b, cond, atol, rtol, k, name=""):
@@ -142,8 +163,11 @@ def assert_close_cond(a, b, cond, atol, rtol, k, name=""):
     c = cond if cond.ndim == a.ndim else cond[..., None]
     tol = atol + rtol * np.abs(b) + k * EPS32 * c
     bad = np.abs(a - b) > tol
-    assert not bad.any(), "%s: %d elements outside atol=%g rtol=%g k=%g (worst excess %.3g at cond %.3g)" % (
-        name, int(bad.sum()), atol, rtol, k, float((np.abs(a - b) - tol).max()), float(np.broadcast_to(c, a.shape)[bad].max()))
+    if bad.any():
+        i = np.unravel_index(np.argmax(np.abs(a - b) - tol), a.shape)
+        raise AssertionError("%s: %d elements outside atol=%g rtol=%g k=%g; worst at %s: got %.9g want %.9g tol %.3g cond %.3g (needs k >= %.1f)" % (
+            name, int(bad.sum()), atol, rtol, k, i, a[i], b[i], tol[i], np.broadcast_to(c, a.shape)[i],
+            float(((np.abs(a - b) - atol - rtol * np.abs(b)) / (EPS32 * np.maximum(np.broadcast_to(c, a.shape), 1e-300)))[bad].max())))
 
 
 def mip_level_f64(uv_da, bias, tex_w, tex_h, max_level):
@@ -167,7 +191,8 @@ def texture_knife_edges(uv, uv_da, bias, tex_shape, filter_mode, boundary_mode, 
     result by a finite amount:
       level: continuous mip level within `level_eps` of an integer inside [0, max_level], or of the clamp ends (the GPU
              evaluates it with the approximate __log2f, SURVEY 8(d)); relevant to every output of the mipmapped modes;
-      texel: u*w - 0.5 (or v*h - 0.5) within `texel_eps` of an integer on a level the pixel uses: the bilinear footprint
+      texel: u*w - 0.5 (or v*h - 0.5) within `texel_eps` of -- but not exactly on -- an integer on a level the pixel uses (an
+             exact hit is computed exactly by both implementations: fp32 products are correctly rounded): the bilinear footprint
              moves to the next texel quad there; the colour is continuous but d(colour)/d(uv) is not, relevant to g_uv,
              g_uv_da, and -- through which texels receive the (vanishing) weight -- irrelevant to g_tex.
     Returns (level_mask, texel_mask), each [N,H,W] bool."""
@@ -191,12 +216,14 @@ def texture_knife_edges(uv, uv_da, bias, tex_shape, filter_mode, boundary_mode, 
                 if boundary_mode == "wrap":
                     x = x - np.floor(x)
                 x = x * s - 0.5
-                texel_mask |= uses & (np.abs(x - np.round(x)) < texel_eps * max(1.0, s / 64.0))
+                d = np.abs(x - np.round(x))
+                texel_mask |= uses & (d > 0) & (d < texel_eps * max(1.0, s / 64.0))
     else:
         for c, s in ((0, tw), (1, th)):
             x = uv[..., c]
             if boundary_mode == "wrap":
                 x = x - np.floor(x)
             x = x * s
-            texel_mask |= np.abs(x - np.round(x)) < texel_eps
+            d = np.abs(x - np.round(x))
+            texel_mask |= (d > 0) & (d < texel_eps)
     return level_mask, texel_mask
