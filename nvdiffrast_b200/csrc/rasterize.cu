@@ -287,7 +287,8 @@ static __device__ __forceinline__ Edge make_edge(int ax, int ay, int bx, int by,
 #define BIN_LIST   256          // triangles set up in shared memory at a time (longer per-bin lists are processed in chunks)
 #define BIN_IDX    2048         // records scanned per segment = capacity of the per-bin index list
 #define BIN_THREADS 256
-#define BIN_MAXCHUNK 1024       // chunk boxes per image that fit the staging area: the BINS path takes at most 32768 triangles per image
+#define B200DR_BINS_MAX_TRIS 49152
+#define BIN_MAXCHUNK 1024       // chunk boxes staged per TMA slab (32768 triangles); larger images re-stage
 
 struct __align__(16) BinTri     // 64 bytes, broadcast-read by every thread of the CTA
 {
@@ -964,10 +965,12 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 extern "C" int b200dr_rasterize_pick_path(int N, int max_tris, int H, int W)
 {
-    // BINS scans max_tris bbox entries per 64x64 bin: cheap while the per-image triangle count is modest.
-    // Heavy geometry (>= 32k triangles per image) goes triangle-parallel.
+    // Measured sweep at 2048^2 x 16 images (scripts/tri_sweep.py, profiles/r02_tri_sweep.json; ms per launch, BINS / SCATTER):
+    //   12 tris 0.31 / 13.9   1 k 0.40 / 2.6   5.9 k 0.55 / 1.4   12 k 0.68 / 1.4   30 k 1.06 / 1.46   100 k 2.5 / 1.9   1 M 17.7 / 1.27
+    // BINS (CTA per 64x64 bin over chunked bounding boxes) costs grow with the triangles per bin, SCATTER (fused setup + 64-bit
+    // atomicMin) gets cheaper per triangle as triangles shrink: they cross between 30 k and 100 k triangles per image.
     (void)N; (void)H; (void)W;
-    return (max_tris <= 32768) ? B200DR_RAST_BINS : B200DR_RAST_SCATTER;
+    return (max_tris <= B200DR_BINS_MAX_TRIS) ? B200DR_RAST_BINS : B200DR_RAST_SCATTER;
 }
 
 extern "C" size_t b200dr_rasterize_scratch_bytes(int N, int max_tris, int H, int W, int path)
