@@ -218,12 +218,10 @@ class Pipeline:
             out = mod.antialias(color, rast, pos, self.tri, topology_hash=self.topo)
         else:
             out, _ = mod.interpolate(leaves["attr"][None], rast, self.tri)
-        if with_loss:
-            loss = torch.dot(out.reshape(-1), self.dy.reshape(-1))      # scalar loss <out, dy>: one pass over the image
-            loss.backward()
-        else:
-            loss = None
-            out.backward(self.dy)
+        # scalar loss <out, dy> (end-to-end runs read it back): one pass over the image; its gradient w.r.t. out is dy by
+        # construction and is fed straight into backward (same for both arms)
+        loss = torch.dot(out.detach().reshape(-1), self.dy.reshape(-1)) if with_loss else None
+        out.backward(self.dy)
         return loss, self.reducer.finish()
 
 

@@ -341,6 +341,13 @@ static __device__ __forceinline__ void red_add2(float* p, float2 v)
     asm volatile("red.global.v2.f32.add [%0], {%1,%2};" :: "l"(p), "f"(v.x), "f"(v.y) : "memory");
 }
 
+// three consecutive floats at a 4-byte aligned global address: one 64-bit vector reduction on the 8-byte aligned pair + one scalar
+static __device__ __forceinline__ void red_add3(float* p, float a, float b, float c)
+{
+    if ((((uintptr_t)p) & 7) == 0) { red_add2(p, make_float2(a, b)); red_add(p + 2, c); }
+    else                           { red_add(p, a); red_add2(p + 1, make_float2(b, c)); }
+}
+
 // ---- L2 prefetch of a warp's NEXT pixel group (streaming kernels walk their tensors with a fixed grid stride, so the
 // addresses are known one iteration ahead).  Measured on c3 (profiles/r02_experiments.md): the bulk form (UBLKPF.L2, one
 // elected lane, goes through the TMA unit) SLOWS the texture kernels by 3-26 % at two to three 256-512 byte requests per

@@ -473,6 +473,11 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const Interp
                         red_add4(ga0, make_float4(t0[0], t0[1 % A], t0[2 % A], t0[3 % A])); red_add4(ga1, make_float4(t1[0], t1[1 % A], t1[2 % A], t1[3 % A]));
                         red_add4(ga2, make_float4(t2[0], t2[1 % A], t2[2 % A], t2[3 % A]));
                     }
+                    else if (!p.use_smem_acc && A == 3)
+                    {
+                        // 12-byte rows: the 8-byte aligned pair is (0,1) for even vertices and (1,2) for odd ones
+                        red_add3(ga0, t0[0], t0[1 % A], t0[2 % A]); red_add3(ga1, t1[0], t1[1 % A], t1[2 % A]); red_add3(ga2, t2[0], t2[1 % A], t2[2 % A]);
+                    }
                     else
                     {
                         #pragma unroll
