@@ -396,7 +396,7 @@ extern "C" int b200dr_antialias_construct_topology(const int32_t* tri, int T, in
     B200DR_CHECK(scratch && scratch_bytes >= b200dr_topology_scratch_bytes(T), "antialias_construct_topology_hash(): scratch buffer too small");
     B200DR_CHECK(B200DR_ALIGNED16(scratch) && B200DR_ALIGNED16(wings), "antialias_construct_topology_hash(): internal tensor not aligned to int4");
     unsigned long long slots = topology_slots(T);
-    cudaMemsetAsync(scratch, 0, slots * sizeof(EdgeSlot), stream);
+    B200DR_CUDA(cudaMemsetAsync(scratch, 0, slots * sizeof(EdgeSlot), stream), "antialias()");
     int blocks = (T + 255) / 256;
     topology_insert_kernel<<<blocks, 256, 0, stream>>>(tri, T, V, (EdgeSlot*)scratch, slots - 1);
     topology_wings_kernel<<<blocks, 256, 0, stream>>>(tri, T, V, (const EdgeSlot*)scratch, slots - 1, (int4*)wings);
@@ -414,7 +414,7 @@ extern "C" int b200dr_antialias_fwd(const float* color, const float* rast, const
     if (aa_fill(p, "antialias_fwd()", color, rast, pos, tri, N, H, W, C, V, T, instance_mode)) return 1;
     B200DR_CHECK(B200DR_ALIGNED16(work_items), "antialias_fwd(): work_buffer internal tensor not aligned to int4");
     p.wings = (const int4*)wings; p.out = out; p.vec_ok = B200DR_ALIGNED16(color) && B200DR_ALIGNED16(out); p.items = (int4*)work_items; p.counters = work_counters;
-    cudaMemsetAsync(work_counters, 0, 4 * sizeof(int), stream);
+    B200DR_CUDA(cudaMemsetAsync(work_counters, 0, 4 * sizeof(int), stream), "antialias()");
     dim3 grid((W + AA_TILE_W - 1) / AA_TILE_W, (H + AA_TILE_H - 1) / AA_TILE_H, N);
     aa_discontinuity_kernel<<<grid, 256, 0, stream>>>(p);
     B200DR_CHECK_LAUNCH("antialias_fwd(discontinuity)");
@@ -443,7 +443,7 @@ extern "C" int b200dr_antialias_grad(const float* color, const float* rast, cons
         B200DR_CHECK_LAUNCH("antialias_grad(copy)");
     }
     else
-        cudaMemcpyAsync(g_color, dy, n * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+        B200DR_CUDA(cudaMemcpyAsync(g_color, dy, n * sizeof(float), cudaMemcpyDeviceToDevice, stream), "antialias()");
     aa_grad_kernel<<<b200dr_num_sms() * 8, 256, 0, stream>>>(p);
     B200DR_CHECK_LAUNCH("antialias_grad()");
     return 0;

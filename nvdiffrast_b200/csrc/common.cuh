@@ -17,6 +17,11 @@ void b200dr_set_error(const char* fmt, ...);
     do { b200dr_count_launches(1); cudaError_t e_ = cudaGetLastError();                                               \
          if (e_ != cudaSuccess) { b200dr_set_error("%s: Cuda error: %s", name, cudaGetErrorString(e_)); return 1; } } while (0)
 
+// every CUDA runtime call that can fail is checked: B200DR_CUDA(cudaMemsetAsync(...), "op()")
+#define B200DR_CUDA(call, name)                                                                   \
+    do { cudaError_t e_ = (call);                                                                 \
+         if (e_ != cudaSuccess) { b200dr_set_error("%s: Cuda error: %s (%s)", name, cudaGetErrorString(e_), #call); return 1; } } while (0)
+
 #define B200DR_ALIGNED16(p) ((((uintptr_t)(p)) & 15) == 0)
 
 void b200dr_count_launches(int n);

@@ -601,12 +601,12 @@ extern "C" int b200dr_interpolate_fwd(const float* attr, const float* rast, cons
     dim3 grid(gx, N);
     if (da)
     {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(interpolate_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (smem > 48 * 1024) B200DR_CUDA(cudaFuncSetAttribute(interpolate_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "interpolate()");
         interpolate_fwd_kernel<true><<<grid, IP_THREADS, smem, stream>>>(p);
     }
     else
     {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(interpolate_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (smem > 48 * 1024) B200DR_CUDA(cudaFuncSetAttribute(interpolate_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "interpolate()");
         interpolate_fwd_kernel<false><<<grid, IP_THREADS, smem, stream>>>(p);
     }
     B200DR_CHECK_LAUNCH("interpolate_fwd()");
@@ -639,14 +639,14 @@ extern "C" int b200dr_interpolate_grad(const float* attr, const float* rast, con
         if (smem_f > 48 * 1024)
         {
             switch (A * 2 + (da ? 1 : 0)) {
-            case 2: cudaFuncSetAttribute(interpolate_grad_fast<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
-            case 3: cudaFuncSetAttribute(interpolate_grad_fast<1, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
-            case 4: cudaFuncSetAttribute(interpolate_grad_fast<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
-            case 5: cudaFuncSetAttribute(interpolate_grad_fast<2, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
-            case 6: cudaFuncSetAttribute(interpolate_grad_fast<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
-            case 7: cudaFuncSetAttribute(interpolate_grad_fast<3, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
-            case 8: cudaFuncSetAttribute(interpolate_grad_fast<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
-            case 9: cudaFuncSetAttribute(interpolate_grad_fast<4, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); break;
+            case 2: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
+            case 3: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<1, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
+            case 4: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
+            case 5: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<2, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
+            case 6: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
+            case 7: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<3, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
+            case 8: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
+            case 9: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<4, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
             }
         }
         // shared accumulators: exactly the resident wave (every CTA zeroes and flushes V*A sums once), rounded DOWN so that no
@@ -673,12 +673,12 @@ extern "C" int b200dr_interpolate_grad(const float* attr, const float* rast, con
     dim3 grid(gx, N);
     if (da)
     {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(interpolate_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (smem > 48 * 1024) B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "interpolate()");
         interpolate_grad_kernel<true><<<grid, IP_THREADS, smem, stream>>>(p);
     }
     else
     {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(interpolate_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (smem > 48 * 1024) B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "interpolate()");
         interpolate_grad_kernel<false><<<grid, IP_THREADS, smem, stream>>>(p);
     }
     B200DR_CHECK_LAUNCH("interpolate_grad()");

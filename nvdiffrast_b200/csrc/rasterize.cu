@@ -1029,7 +1029,7 @@ extern "C" int b200dr_rasterize_fwd(const float* pos, const int32_t* tri, const 
     else
     {
         p.keys = (unsigned long long*)scratch;
-        cudaMemsetAsync(p.keys, 0xFF, (size_t)N * H * W * sizeof(unsigned long long), stream);
+        B200DR_CUDA(cudaMemsetAsync(p.keys, 0xFF, (size_t)N * H * W * sizeof(unsigned long long), stream), "rasterize()");
     }
 
     // Viewports larger than 2048 px are rendered as a grid of <= 2048^2 sub-viewports (the snapped coordinates are S16):
@@ -1051,7 +1051,7 @@ extern "C" int b200dr_rasterize_fwd(const float* pos, const int32_t* tri, const 
         p.vyo = (float)(H - p.vpH - 2 * p.offY) / (float)p.vpH;
         if (path == B200DR_RAST_BINS)
         {
-            cudaMemsetAsync(p.extra, 0, (size_t)N * sizeof(int), stream);
+            B200DR_CUDA(cudaMemsetAsync(p.extra, 0, (size_t)N * sizeof(int), stream), "rasterize()");
             raster_setup_kernel<<<dim3((max_tris + 127) / 128, N), 128, 0, stream>>>(p);
             B200DR_CHECK_LAUNCH("rasterize_fwd(setup)");
             dim3 grid((p.vpW + BIN_SIZE - 1) / BIN_SIZE, (p.vpH + BIN_SIZE - 1) / BIN_SIZE, N);
@@ -1114,12 +1114,12 @@ extern "C" int b200dr_rasterize_grad(const float* pos, const int32_t* tri, const
     size_t dyn = p.use_smem ? smem : 0;
     if (ddb)
     {
-        if (dyn > 48 * 1024) cudaFuncSetAttribute(raster_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (dyn > 48 * 1024) B200DR_CUDA(cudaFuncSetAttribute(raster_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "rasterize()");
         raster_grad_kernel<true><<<grid, 256, dyn, stream>>>(p);
     }
     else
     {
-        if (dyn > 48 * 1024) cudaFuncSetAttribute(raster_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (dyn > 48 * 1024) B200DR_CUDA(cudaFuncSetAttribute(raster_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "rasterize()");
         raster_grad_kernel<false><<<grid, 256, dyn, stream>>>(p);
     }
     B200DR_CHECK_LAUNCH("rasterize_grad()");

@@ -1966,7 +1966,7 @@ extern "C" int b200dr_texture_fwd(const float* tex, const float* const* mip_ptrs
     size_t smem = (size_t)TEX_THREADS * C * sizeof(float);
     p.staged = smem <= 96 * 1024;
     if (!p.staged) smem = 0;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(texture_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (smem > 48 * 1024) B200DR_CUDA(cudaFuncSetAttribute(texture_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "texture()");
     int grid = p.chunks;
     int cap = b200dr_num_sms() * 16;
     if (grid > cap) grid = cap;
@@ -2009,7 +2009,7 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
     p.g_bias = (filter_mode == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && mip_level_bias) ? g_bias : 0;
 
     // padded gradient pyramid
-    cudaMemsetAsync(scratch, 0, need, stream);
+    B200DR_CUDA(cudaMemsetAsync(scratch, 0, need, stream), "texture()");
     ResolveParams r = {};
     {
         char* s = (char*)scratch;
@@ -2048,7 +2048,7 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
         size_t smem = (size_t)TEX_THREADS * C * sizeof(float);
         p.staged = smem <= 96 * 1024;
         if (!p.staged) smem = 0;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(texture_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (smem > 48 * 1024) B200DR_CUDA(cudaFuncSetAttribute(texture_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "texture()");
         int grid = p.chunks;
         int cap = b200dr_num_sms() * 16;
         if (grid > cap) grid = cap;
