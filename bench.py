@@ -487,6 +487,51 @@ def target_kernels(mod, device, peak, n_img=16, res=2048):
     return out
 
 
+def envphong_shaped(mod, device, peak, n_img=4, res=1024, face=512, C=3):
+    """Cube-map texturing at the shape of the reference's envphong sample (6 x 512^2 x 3 environment map sampled trilinearly
+    by reflection-like directions over a 1024^2 image): a unit sphere's normals inside the silhouette, one
+    constant direction outside; texture forward + backward timed per C-ABI op."""
+    from nvdiffrast_b200 import _lib
+    g = torch.Generator(device=device); g.manual_seed(11)
+    tex = torch.rand((1, 6, face, face, C), device=device, generator=g)
+    ys, xs = torch.meshgrid(torch.linspace(-1.2, 1.2, res, device=device), torch.linspace(-1.2, 1.2, res, device=device), indexing="ij")
+    r2 = xs * xs + ys * ys
+    inside = r2 < 1.0
+    z = torch.sqrt(torch.clamp(1.0 - r2, min=1e-4))
+    d = torch.stack([torch.where(inside, xs, torch.zeros_like(xs)), torch.where(inside, ys, torch.zeros_like(ys)), torch.where(inside, z, torch.ones_like(z))], -1)
+    px = 2.4 / res
+    dX = torch.stack([torch.full_like(xs, px), torch.zeros_like(xs), -xs / z * px], -1) * inside[..., None]
+    dY = torch.stack([torch.zeros_like(xs), torch.full_like(xs, px), -ys / z * px], -1) * inside[..., None]
+    uv = d[None].repeat(n_img, 1, 1, 1).contiguous()
+    uv_da = torch.stack([dX[..., 0], dY[..., 0], dX[..., 1], dY[..., 1], dX[..., 2], dY[..., 2]], -1)[None].repeat(n_img, 1, 1, 1).contiguous()
+    dy = torch.randn((n_img, res, res, C), device=device, generator=g)
+    mip = mod.texture_construct_mip(tex, cube_mode=True)
+    P = n_img * res * res
+    nbytes = {"b200dr_texture_fwd": (12 + 4 * C + 24) * P, "b200dr_texture_grad": (24 + 4 * C + 48) * P}
+
+    def step():
+        t = tex.detach().requires_grad_(True); u = uv.detach().requires_grad_(True); da = uv_da.detach().requires_grad_(True)
+        o = mod.texture(t, u, da, mip=mip, filter_mode="linear-mipmap-linear", boundary_mode="cube")
+        o.backward(dy)
+
+    for _ in range(3):
+        step()
+    trace = []
+    _lib.set_trace(trace)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); it = 0
+    while time.perf_counter() - t0 < 0.4 or it < 10:
+        step(); it += 1
+        if it % 10 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    _lib.set_trace(None)
+    table, _ = ops_table(trace, it, nbytes, peak)
+    return {"workload": "envphong-shaped: cube map 6x%d^2x%d, %d^2, %d images, trilinear, fwd+bwd of texture()" % (face, C, res, n_img),
+            "coverage": float(inside.float().mean()),
+            "ops": {k: {"ms": v["ms"], "bytes_per_pixel": nbytes["b200dr_" + k] // P, "frac": v.get("frac")} for k, v in table.items() if "frac" in v}}
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -612,6 +657,7 @@ def main():
             torch.cuda.empty_cache()
             out["target_kernels"] = target_kernels(mod, device, peak)
             out["other_configs"] = {name: side_config(mod, name, K, W, device, peak) for name in ("c2", "c4", "c5")}
+            out["other_configs"]["envphong_shaped"] = envphong_shaped(mod, device, peak)
     if not args.no_cpu_baseline and world == 1:
         ns = {"c3": 12, "c5": 12, "c2": 16, "c4": 1}[workload]       # bounded sample: ~10 s of host time
         rate, dt, thr = cpu_oracle_rate(workload, res, ns)

@@ -1505,101 +1505,147 @@ __global__ void __launch_bounds__(256) texture_cube_fwd_kernel(const TexParams p
     }
 }
 
+// One bilinear tap of the cube gradient scatter, warp-cooperative (every lane calls; inactive lanes pass tc = -1).  Rendered
+// images contain regions whose pixels land on the same texel (a constant background direction; strongly magnified maps):
+// `reduce` sums runs of equal (level, texel) across consecutive lanes first, so a texel receives one vector reduction per run
+// instead of one same-address atomic per pixel (those serialise chip-wide).
+template <int C>
+static __device__ __forceinline__ void cube_scatter_warp(float* g, int level, int tc, float w, const float (&dy)[C], bool reduce)
+{
+    if (!reduce) { scatter_tap<C>(g, tc, w, dy); return; }
+    const WarpRuns runs = warp_runs(tc >= 0 ? (tc ^ (level << 27)) : -1 - (int)(threadIdx.x & 31));
+    float v[C];
+    #pragma unroll
+    for (int i = 0; i < C; i++) v[i] = warp_run_sum(tc >= 0 ? w * dy[i] : 0.f, runs);
+    if (runs.is_head) scatter_tap<C>(g, tc, 1.f, v);
+}
+
 template <int C>
 __global__ void __launch_bounds__(256) texture_cube_grad_kernel(const TexParams p)
 {
     const TexMode m = tex_mode(p);
     const size_t hw = (size_t)p.H * p.W, total = hw * p.N;
     const bool trilinear = (m.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
-    for (size_t pidx = (size_t)blockIdx.x * 256 + threadIdx.x; pidx < total; pidx += (size_t)gridDim.x * 256)
+    const int lane = threadIdx.x & 31;
+    // whole warps iterate together (warp collectives in the scatter): the loop runs over 32-pixel groups
+    for (size_t base = ((size_t)blockIdx.x * 256 + threadIdx.x) - lane; base < total; base += (size_t)gridDim.x * 256)
     {
+        const size_t pidx = base + lane;
+        const bool inb = pidx < total;
         float dy[C];
         unsigned dmax = 0u;
         #pragma unroll
-        for (int i = 0; i < C; i++) { dy[i] = p.dy[pidx * C + i]; dmax |= __float_as_uint(dy[i]); }
+        for (int i = 0; i < C; i++) { dy[i] = inb ? p.dy[pidx * C + i] : 0.f; dmax |= __float_as_uint(dy[i]); }
+        const bool act = inb && (__uint_as_float(dmax) != 0.f);
         float3 g_v = make_float3(0.f, 0.f, 0.f), g0 = g_v, g1 = g_v;
         float df = 0.f;
-        if (__uint_as_float(dmax) != 0.f)
+        // per-lane footprint; inactive lanes keep tc = -1 and flow through the warp-cooperative scatter
+        int level0 = 0, level1 = 0; float flevel = 0.f; float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
+        int4 tc0 = make_int4(-1, -1, -1, -1), tc1 = tc0; bool cor0 = false, cor1 = false;
+        float2 uv0 = make_float2(0.f, 0.f), uv1 = uv0;
+        float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+        float3 v = make_float3(0.f, 0.f, 1.f), dX = make_float3(0.f, 0.f, 0.f), dY = dX, dfdv = dX;
+        bool two = false; float f0 = 1.f;
+        if (act)
         {
             int tz = (p.texD == 1) ? 0 : (int)(pidx / hw);
-            float3 v, dX, dY;
             cube_load_dirs(p, pidx, v, dX, dY);
-            if (m.filter == B200DR_FILTER_NEAREST) scatter_tap<C>(p.gpad[0], cube_nearest(p, v, tz), 1.f, dy);
+            if (m.filter == B200DR_FILTER_NEAREST) { tc0.x = cube_nearest(p, v, tz); w0.x = 1.f; }
             else
             {
-                int level0, level1; float flevel; float4 dw = make_float4(0.f, 0.f, 0.f, 0.f);
                 float bias = p.bias ? ld_stream_f(p.bias + pidx) : 0.f;
                 mip_level_from<true>(p, m, cube_grad_st(v, dX, dY), bias, level0, level1, flevel, dw);
-                float3 dfdv = make_float3(0.f, 0.f, 0.f);
                 if (trilinear && p.uv_da)
                 {
                     dfdv = cube_grad2_dot(v, dX, dY, dw);
                     if (!isfinite(dfdv.x) || !isfinite(dfdv.y) || !isfinite(dfdv.z)) { dfdv = make_float3(0.f, 0.f, 0.f); dw = make_float4(0.f, 0.f, 0.f, 0.f); }
                 }
-                bool two = trilinear && (flevel > 0.f);
-                float f0 = trilinear ? (1.f - flevel) : 1.f;
-                float gu = 0.f, gv = 0.f;
-                int4 tc0; bool cor0;
-                float2 uv0 = cube_index_linear(p, v, tz, level0, tc0, cor0);
-                {
-                    float uv011 = uv0.x * uv0.y, uv010 = uv0.x - uv011, uv001 = uv0.y - uv011, uv000 = 1.f - uv0.x - uv001;
-                    float4 w = cube_weights(make_float4(uv000 * f0, uv010 * f0, uv001 * f0, uv011 * f0), tc0, cor0);
-                    float* gp = p.gpad[level0];
-                    scatter_tap<C>(gp, tc0.x, w.x, dy); scatter_tap<C>(gp, tc0.y, w.y, dy);
-                    scatter_tap<C>(gp, tc0.z, w.z, dy); scatter_tap<C>(gp, tc0.w, w.w, dy);
-                }
-                float4 A00, A10, A01, A11;
-                cube_fetch(p.tex[level0], tc0, cor0, A00, A10, A01, A11);
-                float a00[C], a10[C], a01[C], a11[C];
-                unpack4<C>(A00, a00); unpack4<C>(A10, a10); unpack4<C>(A01, a01); unpack4<C>(A11, a11);
-                float sclu0 = (float)lvl_w(p, level0);
-                #pragma unroll
-                for (int i = 0; i < C; i++)
-                {
-                    float dy0 = f0 * dy[i];
-                    float ad = (a11[i] + a00[i] - a10[i] - a01[i]);
-                    gu += dy0 * ((a10[i] - a00[i]) + uv0.y * ad) * sclu0;
-                    gv += dy0 * ((a01[i] - a00[i]) + uv0.x * ad) * sclu0;
-                }
+                two = trilinear && (flevel > 0.f);
+                f0 = trilinear ? (1.f - flevel) : 1.f;
+                uv0 = cube_index_linear(p, v, tz, level0, tc0, cor0);
+                float uv011 = uv0.x * uv0.y, uv010 = uv0.x - uv011, uv001 = uv0.y - uv011, uv000 = 1.f - uv0.x - uv001;
+                w0 = cube_weights(make_float4(uv000 * f0, uv010 * f0, uv001 * f0, uv011 * f0), tc0, cor0);
                 if (two)
                 {
-                    int4 tc1; bool cor1;
-                    float2 uv1 = cube_index_linear(p, v, tz, level1, tc1, cor1);
+                    uv1 = cube_index_linear(p, v, tz, level1, tc1, cor1);
                     float uv111 = uv1.x * uv1.y, uv110 = uv1.x - uv111, uv101 = uv1.y - uv111, uv100 = 1.f - uv1.x - uv101;
-                    float4 w = cube_weights(make_float4(uv100 * flevel, uv110 * flevel, uv101 * flevel, uv111 * flevel), tc1, cor1);
-                    float* gp = p.gpad[level1];
-                    scatter_tap<C>(gp, tc1.x, w.x, dy); scatter_tap<C>(gp, tc1.y, w.y, dy);
-                    scatter_tap<C>(gp, tc1.z, w.z, dy); scatter_tap<C>(gp, tc1.w, w.w, dy);
-                    float4 B00, B10, B01, B11;
-                    cube_fetch(p.tex[level1], tc1, cor1, B00, B10, B01, B11);
-                    float b00[C], b10[C], b01[C], b11[C];
-                    unpack4<C>(B00, b00); unpack4<C>(B10, b10); unpack4<C>(B01, b01); unpack4<C>(B11, b11);
-                    float sclu1 = (float)lvl_w(p, level1);
-                    #pragma unroll
-                    for (int i = 0; i < C; i++)
-                    {
-                        float dy1 = flevel * dy[i];
-                        float bd = (b11[i] + b00[i] - b10[i] - b01[i]);
-                        gu += dy1 * ((b10[i] - b00[i]) + uv1.y * bd) * sclu1;
-                        gv += dy1 * ((b01[i] - b00[i]) + uv1.x * bd) * sclu1;
-                        df += (bilerp(b00[i], b10[i], b01[i], b11[i], uv1) - bilerp(a00[i], a10[i], a01[i], a11[i], uv0)) * dy[i];
-                    }
+                    w1 = cube_weights(make_float4(uv100 * flevel, uv110 * flevel, uv101 * flevel, uv111 * flevel), tc1, cor1);
                 }
-                g_v = cube_grad(v, gu, gv);
-                if (trilinear) { g_v.x += dfdv.x * df; g_v.y += dfdv.y * df; g_v.z += dfdv.z * df; }
-                if (trilinear && p.uv_da)
+                else tc1 = make_int4(-1, -1, -1, -1);
+            }
+        }
+        // ---- texel gradients, warp-uniform control flow
+        if (__any_sync(0xffffffffu, act))
+        {
+            const bool reduce = __popc(warp_runs(act ? (tc0.x ^ (level0 << 27)) : -1 - lane).heads) <= 12;   // few distinct texels in this group
+            float* gp0 = p.gpad[level0];        // level differs per lane: the key carries it, the pointer is the lane's own
+            cube_scatter_warp<C>(gp0, level0, tc0.x, w0.x, dy, reduce);
+            if (m.filter != B200DR_FILTER_NEAREST)
+            {
+                cube_scatter_warp<C>(gp0, level0, tc0.y, w0.y, dy, reduce);
+                cube_scatter_warp<C>(gp0, level0, tc0.z, w0.z, dy, reduce);
+                cube_scatter_warp<C>(gp0, level0, tc0.w, w0.w, dy, reduce);
+                if (__any_sync(0xffffffffu, two))
                 {
-                    g0 = cube_grad(v, dw.x * df, dw.z * df);
-                    g1 = cube_grad(v, dw.y * df, dw.w * df);
+                    float* gp1 = p.gpad[level1];
+                    cube_scatter_warp<C>(gp1, level1, tc1.x, w1.x, dy, reduce);
+                    cube_scatter_warp<C>(gp1, level1, tc1.y, w1.y, dy, reduce);
+                    cube_scatter_warp<C>(gp1, level1, tc1.z, w1.z, dy, reduce);
+                    cube_scatter_warp<C>(gp1, level1, tc1.w, w1.w, dy, reduce);
                 }
             }
         }
-        if (p.g_uv) { p.g_uv[pidx * 3] = g_v.x; p.g_uv[pidx * 3 + 1] = g_v.y; p.g_uv[pidx * 3 + 2] = g_v.z; }
-        if (p.g_bias) p.g_bias[pidx] = df;
-        if (p.g_uv_da)
+        // ---- direction / level gradients
+        if (act && m.filter != B200DR_FILTER_NEAREST)
         {
-            float2* q = (float2*)p.g_uv_da + pidx * 3;
-            q[0] = make_float2(g0.x, g1.x); q[1] = make_float2(g0.y, g1.y); q[2] = make_float2(g0.z, g1.z);
+            float gu = 0.f, gv = 0.f;
+            float4 A00, A10, A01, A11;
+            cube_fetch(p.tex[level0], tc0, cor0, A00, A10, A01, A11);
+            float a00[C], a10[C], a01[C], a11[C];
+            unpack4<C>(A00, a00); unpack4<C>(A10, a10); unpack4<C>(A01, a01); unpack4<C>(A11, a11);
+            float sclu0 = (float)lvl_w(p, level0);
+            #pragma unroll
+            for (int i = 0; i < C; i++)
+            {
+                float dy0 = f0 * dy[i];
+                float ad = (a11[i] + a00[i] - a10[i] - a01[i]);
+                gu += dy0 * ((a10[i] - a00[i]) + uv0.y * ad) * sclu0;
+                gv += dy0 * ((a01[i] - a00[i]) + uv0.x * ad) * sclu0;
+            }
+            if (two)
+            {
+                float4 B00, B10, B01, B11;
+                cube_fetch(p.tex[level1], tc1, cor1, B00, B10, B01, B11);
+                float b00[C], b10[C], b01[C], b11[C];
+                unpack4<C>(B00, b00); unpack4<C>(B10, b10); unpack4<C>(B01, b01); unpack4<C>(B11, b11);
+                float sclu1 = (float)lvl_w(p, level1);
+                #pragma unroll
+                for (int i = 0; i < C; i++)
+                {
+                    float dy1 = flevel * dy[i];
+                    float bd = (b11[i] + b00[i] - b10[i] - b01[i]);
+                    gu += dy1 * ((b10[i] - b00[i]) + uv1.y * bd) * sclu1;
+                    gv += dy1 * ((b01[i] - b00[i]) + uv1.x * bd) * sclu1;
+                    df += (bilerp(b00[i], b10[i], b01[i], b11[i], uv1) - bilerp(a00[i], a10[i], a01[i], a11[i], uv0)) * dy[i];
+                }
+            }
+            g_v = cube_grad(v, gu, gv);
+            if (trilinear) { g_v.x += dfdv.x * df; g_v.y += dfdv.y * df; g_v.z += dfdv.z * df; }
+            if (trilinear && p.uv_da)
+            {
+                g0 = cube_grad(v, dw.x * df, dw.z * df);
+                g1 = cube_grad(v, dw.y * df, dw.w * df);
+            }
+        }
+        if (inb)
+        {
+            if (p.g_uv) { p.g_uv[pidx * 3] = g_v.x; p.g_uv[pidx * 3 + 1] = g_v.y; p.g_uv[pidx * 3 + 2] = g_v.z; }
+            if (p.g_bias) p.g_bias[pidx] = df;
+            if (p.g_uv_da)
+            {
+                float2* q = (float2*)p.g_uv_da + pidx * 3;
+                q[0] = make_float2(g0.x, g1.x); q[1] = make_float2(g0.y, g1.y); q[2] = make_float2(g0.z, g1.z);
+            }
         }
     }
 }

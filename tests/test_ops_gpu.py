@@ -482,6 +482,34 @@ def test_texture_cube_vs_reference(dr, ref, case):
             assert_close(got[k], rgot[k], 1e-3, tol, k + " vs ref", max_bad_frac=5e-3)
 
 
+@pytest.mark.parametrize("filter_mode", ["linear", "linear-mipmap-linear"])
+@pytest.mark.parametrize("C", [3, 6])
+def test_texture_cube_constant_direction_regions(dr, filter_mode, C):
+    """Images with large regions of one constant direction (a background) next to varying ones: every pixel of a region lands
+    on the same texels, which exercises the warp-level run merging of the cube gradient scatter (C <= 4) and the generic
+    multi-group kernels (C = 6)."""
+    rng = np.random.default_rng(37)
+    N, H, W = 2, 48, 80
+    tex = rng.uniform(size=(1, 6, 16, 16, C)).astype(np.float32)
+    uv = rng.normal(size=(N, H, W, 3)).astype(np.float32)
+    uv[0, :20] = (0.3, -0.2, 1.0); uv[1, 10:40, 16:64] = (-1.0, 0.15, 0.4)          # constant regions, interior of a face
+    uv[0, 30:40] = (1.0, 1.0, 0.2)                                                    # constant region on a face seam
+    mip = "mipmap" in filter_mode
+    uv_da = (rng.normal(size=(N, H, W, 6)) * 0.02).astype(np.float32) if mip else None
+    if mip:
+        uv_da[0, :20] = 0.0; uv_da[1, 10:40, 16:64] = 0.01
+    ttex = cu(tex).requires_grad_(True); tuv = cu(uv).requires_grad_(True)
+    tda = cu(uv_da).requires_grad_(True) if mip else None
+    out = dr.texture(ttex, tuv, tda, filter_mode=filter_mode, boundary_mode="cube")
+    oo = oracle.texture_fwd(tex, uv, uv_da, None, filter_mode=filter_mode, boundary_mode="cube")
+    assert_close(out.detach().cpu().numpy(), oo, 2e-5, 1e-4, "cube out", max_bad_frac=2e-3)
+    dy = _rand_like(out.shape, 38)
+    (out * cu(dy)).sum().backward()
+    g = oracle.texture_grad(tex, uv, dy, uv_da, None, filter_mode=filter_mode, boundary_mode="cube")
+    assert_grad_close(ttex.grad.cpu().numpy(), g["g_tex"], 2e-3, "g_tex")
+    assert_close(tuv.grad.cpu().numpy(), g["g_uv"], 1e-3, 2e-3, "g_uv", max_bad_frac=5e-3)
+
+
 def test_texture_cube_mip_wrapper_and_errors(dr):
     rng = np.random.default_rng(31)
     tex = rng.uniform(size=(2, 6, 16, 16, 3)).astype(np.float32)
