@@ -391,8 +391,11 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(const RastParams p)
 static __device__ __forceinline__ int s16lo(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
 static __device__ __forceinline__ int s16hi(uint32_t v) { return (int)v >> 16; }
 
+#ifndef BIN_MINB
+#define BIN_MINB 1
+#endif
 template <bool PEEL_IN, bool DEPTH_OUT>
-__global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastParams p)
+__global__ void __launch_bounds__(BIN_THREADS, BIN_MINB) raster_bins_kernel(const RastParams p)
 {
     __shared__ BinTri   s_tri[BIN_LIST];            // 16 KB
     __shared__ int      s_idx[BIN_IDX];             //  8 KB
@@ -416,9 +419,12 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
 
     if (tid == 0) mbar_init(&s_mbar, 1);
 
-    uint32_t bestD[16], bestI[16], peelD[16];
+    // best visibility key of each of the thread's 16 pixels: (depth << 32) | ~id.  "Nearer depth wins, equal depth: the later
+    // triangle wins" (impl/FineRaster.inl:344-361, 152-172) is the unsigned 64-bit order of these keys; empty = (DEPTH_MAX, id 0).
+    unsigned long long best[16];
+    uint32_t peelD[16];
     #pragma unroll
-    for (int i = 0; i < 16; i++) { bestD[i] = DR_DEPTH_MAX; bestI[i] = 0u; }
+    for (int i = 0; i < 16; i++) best[i] = ((unsigned long long)DR_DEPTH_MAX << 32) | 0xFFFFFFFFull;
     if (PEEL_IN)
     {
         #pragma unroll
@@ -569,7 +575,7 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
                 if ((e2 + 3 * max(e2sx, 0) + 3 * max(e2sy, 0)) < 0) continue;
                 uint32_t zx = (uint32_t)q2.z, zy = (uint32_t)q2.w;
                 uint32_t zr = (uint32_t)q2.y + zx * (uint32_t)tx + zy * (uint32_t)ty;
-                uint32_t id = (uint32_t)q3.x;
+                const uint32_t nid = 0xFFFFFFFFu - (uint32_t)q3.x;
                 #pragma unroll
                 for (int j = 0; j < 4; j++)
                 {
@@ -578,13 +584,11 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
                     #pragma unroll
                     for (int i = 0; i < 4; i++)
                     {
-                        if ((f0 | f1 | f2) >= 0)
-                        {
-                            const int sidx = j * 4 + i;
-                            bool pass = (z < bestD[sidx]) || (z == bestD[sidx] && id > bestI[sidx]);
-                            if (PEEL_IN) pass = pass && (z > peelD[sidx]);
-                            if (pass) { bestD[sidx] = z; bestI[sidx] = id; }
-                        }
+                        const int sidx = j * 4 + i;
+                        const unsigned long long key = ((unsigned long long)z << 32) | nid;
+                        bool pass = ((f0 | f1 | f2) >= 0) && (key < best[sidx]);
+                        if (PEEL_IN) pass = pass && (z > peelD[sidx]);
+                        if (pass) best[sidx] = key;
                         f0 += e0sx; f1 += e1sx; f2 += e2sx; z += zx;
                     }
                     e0 += e0sy; e1 += e1sy; e2 += e2sy; zr += zy;
@@ -600,7 +604,7 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
     // ---- hand the winners to the shader phase through shared memory (transposes 4x4 blocks to row order)
     #pragma unroll
     for (int j = 0; j < 4; j++)
-        *(uint4*)&s_ids[(ty + j) * BIN_SIZE + tx] = make_uint4(bestI[j * 4 + 0], bestI[j * 4 + 1], bestI[j * 4 + 2], bestI[j * 4 + 3]);
+        *(uint4*)&s_ids[(ty + j) * BIN_SIZE + tx] = make_uint4(~(uint32_t)best[j * 4 + 0], ~(uint32_t)best[j * 4 + 1], ~(uint32_t)best[j * 4 + 2], ~(uint32_t)best[j * 4 + 3]);
 
     if (DEPTH_OUT)
     {
@@ -611,11 +615,11 @@ __global__ void __launch_bounds__(BIN_THREADS) raster_bins_kernel(const RastPara
             if (ly >= p.vpH) continue;
             uint32_t* dst = p.depth_out + ((size_t)n * p.H + p.offY + ly) * p.W + p.offX + lx;
             if (lx + 3 < p.vpW && (p.W & 3) == 0 && (p.offX & 3) == 0)
-                *(uint4*)dst = make_uint4(bestD[j * 4 + 0], bestD[j * 4 + 1], bestD[j * 4 + 2], bestD[j * 4 + 3]);
+                *(uint4*)dst = make_uint4((uint32_t)(best[j * 4 + 0] >> 32), (uint32_t)(best[j * 4 + 1] >> 32), (uint32_t)(best[j * 4 + 2] >> 32), (uint32_t)(best[j * 4 + 3] >> 32));
             else
             {
                 #pragma unroll
-                for (int i = 0; i < 4; i++) if (lx + i < p.vpW) dst[i] = bestD[j * 4 + i];
+                for (int i = 0; i < 4; i++) if (lx + i < p.vpW) dst[i] = (uint32_t)(best[j * 4 + i] >> 32);
             }
         }
     }

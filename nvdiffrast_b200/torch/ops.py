@@ -259,6 +259,11 @@ class _rasterize_func(torch.autograd.Function):
         return None, g_pos, None, None, None, None, None
 
 
+def _cpu_ranges(ranges):
+    """Instanced mode passes an empty [0, 2] int32 CPU tensor down to the op (csrc/torch/torch_rasterize.cpp:60-67)."""
+    return torch.empty(size=(0, 2), dtype=torch.int32, device='cpu') if ranges is None else ranges
+
+
 def rasterize(glctx, pos, tri, resolution, ranges=None, grad_db=True):
     '''Rasterize triangles.
 
@@ -278,11 +283,8 @@ def rasterize(glctx, pos, tri, resolution, ranges=None, grad_db=True):
     assert isinstance(glctx, RasterizeCudaContext)
     assert grad_db is True or grad_db is False
     assert isinstance(pos, torch.Tensor) and isinstance(tri, torch.Tensor)
-    resolution = tuple(resolution)
-    if ranges is None:
-        ranges = torch.empty(size=(0, 2), dtype=torch.int32, device='cpu')
-    else:
-        assert isinstance(ranges, torch.Tensor)
+    assert ranges is None or isinstance(ranges, torch.Tensor)
+    resolution, ranges = tuple(resolution), _cpu_ranges(ranges)
     if glctx.active_depth_peeler is not None:
         # The reference *returns* this error object (nvdiffrast/torch/ops.py:131-132); kept for drop-in behaviour.
         return RuntimeError("Cannot call rasterize() during depth peeling operation, use rasterize_next_layer() instead")
@@ -292,48 +294,53 @@ def rasterize(glctx, pos, tri, resolution, ranges=None, grad_db=True):
 
 
 class DepthPeeler:
+    """Depth peeling: `with DepthPeeler(glctx, pos, tri, resolution) as peeler: rast, db = peeler.rasterize_next_layer()`.
+    Every call returns the next-nearest surface layer (arguments as in `rasterize()`; same protocol and error texts as
+    nvdiffrast/torch/ops.py:141-204).  The context keeps two ping-pong depth layers while a peeler is active: layer k kills
+    fragments at or in front of layer k-1's depth."""
+
     def __init__(self, glctx, pos, tri, resolution, ranges=None, grad_db=True):
-        '''Depth peeler: `with DepthPeeler(...) as peeler: rast, db = peeler.rasterize_next_layer()`.
-        Arguments as in `rasterize()` (nvdiffrast/torch/ops.py:141-204).'''
         assert isinstance(glctx, RasterizeCudaContext)
         assert grad_db is True or grad_db is False
         assert isinstance(pos, torch.Tensor) and isinstance(tri, torch.Tensor)
-        resolution = tuple(resolution)
-        if ranges is None:
-            ranges = torch.empty(size=(0, 2), dtype=torch.int32, device='cpu')
-        else:
-            assert isinstance(ranges, torch.Tensor)
+        assert ranges is None or isinstance(ranges, torch.Tensor)
         self.raster_ctx = glctx
-        self.pos = pos
-        self.tri = tri
-        self.resolution = resolution
-        self.ranges = ranges
-        self.grad_db = grad_db
-        self.peeling_idx = None
+        # everything rasterize_next_layer() forwards, frozen at construction
+        self._args = (pos, tri, tuple(resolution), _cpu_ranges(ranges), grad_db)
+        self._layer = None                              # None: not entered; k: next layer to produce
+
+    # read-only views of the frozen arguments (the reference exposes them as attributes)
+    pos = property(lambda self: self._args[0] if self._args else None)
+    tri = property(lambda self: self._args[1] if self._args else None)
+    resolution = property(lambda self: self._args[2] if self._args else None)
+    ranges = property(lambda self: self._args[3] if self._args else None)
+    grad_db = property(lambda self: self._args[4] if self._args else None)
+    peeling_idx = property(lambda self: self._layer)
 
     def __enter__(self):
-        if self.raster_ctx is None:
+        ctx = self.raster_ctx
+        if ctx is None:
             raise RuntimeError("Cannot re-enter a terminated depth peeling operation")
-        if self.raster_ctx.active_depth_peeler is not None:
+        if ctx.active_depth_peeler is not None:
             raise RuntimeError("Cannot have multiple depth peelers active simultaneously in a rasterization context")
-        self.raster_ctx.active_depth_peeler = self
-        self.peeling_idx = 0
+        ctx.active_depth_peeler = self
+        self._layer = 0
         return self
 
-    def __exit__(self, *args):
+    def __exit__(self, *exc):
         assert self.raster_ctx.active_depth_peeler is self
         self.raster_ctx.active_depth_peeler = None
-        self.raster_ctx = None
-        self.pos = self.tri = self.resolution = self.ranges = self.grad_db = self.peeling_idx = None
+        self.raster_ctx, self._args, self._layer = None, None, None      # terminated: cannot be re-entered
         return None
 
     def rasterize_next_layer(self):
         '''Rasterize the next depth layer: as `rasterize()`, minus the surface points already reported.'''
         assert self.raster_ctx.active_depth_peeler is self
-        assert self.peeling_idx >= 0
-        result = _rasterize_func.apply(self.raster_ctx, self.pos, self.tri, self.resolution, self.ranges, self.grad_db, self.peeling_idx)
-        _Provenance("rasterize", (self.pos, self.tri), result, grad_db=self.grad_db)
-        self.peeling_idx += 1
+        assert self._layer >= 0
+        pos, tri, resolution, ranges, grad_db = self._args
+        result = _rasterize_func.apply(self.raster_ctx, pos, tri, resolution, ranges, grad_db, self._layer)
+        _Provenance("rasterize", (pos, tri), result, grad_db=grad_db)
+        self._layer += 1
         return result
 
 
