@@ -261,8 +261,13 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_kernel(const Inte
 #ifndef ACC_SMEM_MAX_V
 #define ACC_SMEM_MAX_V (1 << 30)
 #endif
-#ifndef IPF_UNROLL
-#define IPF_UNROLL 4        // forward: 4 groups of 32 pixels in flight per warp (A = 3 at 2048^2 x 16: 0.346 -> 0.322 ms; 1: 0.370)
+// forward: groups of 32 pixels in flight per warp.  Without pixel differentials 4 (A = 3 at 2048^2 x 16: 0.346 -> 0.322 ms;
+// 1: 0.370); with them 2 (c3, A = 2 + differentials: 4 groups cost 0.544 -> 0.624 ms in registers)
+#ifndef IPF_UNROLL_PLAIN
+#define IPF_UNROLL_PLAIN 4
+#endif
+#ifndef IPF_UNROLL_DA
+#define IPF_UNROLL_DA 2
 #endif
 #ifndef IPG_UNROLL
 #define IPG_UNROLL 2        // backward: 2 (4: 0.783 -> 0.862 ms, registers spill; 1: 0.835)
@@ -281,6 +286,7 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_fwd_fast(const InterpP
 {
     constexpr int SK = (A == 3) ? (DA ? 6 : 3) : 1;                    // staging floats per pixel (only K = 3 / 6 need it)
     __shared__ __align__(16) float s_stage[IP_THREADS / 32][32 * SK];
+    constexpr int IPF_UNROLL = DA ? IPF_UNROLL_DA : IPF_UNROLL_PLAIN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = blockIdx.y;
     const int hw = p.H * p.W;
@@ -587,7 +593,8 @@ extern "C" int b200dr_interpolate_fwd(const float* attr, const float* rast, cons
     if (fast_ok(p, da, attr) && B200DR_ALIGNED16(out) && (!da || (((uintptr_t)out_da) & 31) == 0))
     {
         int groups = (int)(((size_t)H * W + 31) / 32);
-        int gx = (groups + (IP_THREADS / 32) * IPF_UNROLL - 1) / ((IP_THREADS / 32) * IPF_UNROLL);
+        const int unroll = da ? IPF_UNROLL_DA : IPF_UNROLL_PLAIN;
+        int gx = (groups + (IP_THREADS / 32) * unroll - 1) / ((IP_THREADS / 32) * unroll);
         int capx = (b200dr_num_sms() * 12 + N - 1) / N;
         if (gx > capx) gx = capx;
         if (gx < 1) gx = 1;
