@@ -103,8 +103,11 @@ class _Provenance:
     def __init__(self, kind, inputs, outputs, **meta):
         self.kind, self.inputs, self.meta = kind, inputs, meta
         self.versions = tuple(o._version for o in outputs)
-        for o in outputs:
-            o._b200dr_prov = self
+        # Only outputs that take part in differentiation are tagged: under no_grad (or with no differentiable input) nothing can be
+        # fused, and the record would merely extend the lifetime of the op's inputs to that of its outputs.
+        if _fusion_enabled and torch.is_grad_enabled() and any(o.requires_grad for o in outputs):
+            for o in outputs:
+                o._b200dr_prov = self
 
 
 def _pristine(t, prov, slot):
@@ -633,8 +636,9 @@ def _texture_fwd(tex, uv, uv_da, mip_level_bias, mip_wrapper, mip_stack, filter_
     return out
 
 
-def _texture_grad(tex, uv, dy, uv_da, mip_level_bias, mip_wrapper, mip_stack, filter_mode, boundary_mode):
-    """-> (g_tex, g_uv, g_uv_da, g_mip_level_bias, g_mip_stack) (csrc/torch/torch_texture.cpp:421-691)."""
+def _texture_grad(tex, uv, dy, uv_da, mip_level_bias, mip_wrapper, mip_stack, filter_mode, boundary_mode, need_uv=True, need_da=True, need_bias=True):
+    """-> (g_tex, g_uv, g_uv_da, g_mip_level_bias, g_mip_stack) (csrc/torch/torch_texture.cpp:421-691).
+    need_*: gradients autograd does not ask for are neither allocated nor written (the reference always writes them)."""
     fn = "texture_grad_linear_mipmap_linear"
     lib = _lib.load()
     dev, (N, H, W, D, Ht, Wt, C), enable_mip, has_uv_da, has_bias, level_max, ptrs, keep = \
@@ -645,9 +649,9 @@ def _texture_grad(tex, uv, dy, uv_da, mip_level_bias, mip_wrapper, mip_stack, fi
     has_stack = len(mip_stack) > 0
     with torch.cuda.device(dev):
         g_tex = torch.empty_like(tex)
-        g_uv = torch.empty_like(uv) if filter_mode != 0 else None
-        g_uv_da = torch.empty_like(uv_da) if (filter_mode == 3 and has_uv_da) else None
-        g_bias = torch.empty_like(mip_level_bias) if (filter_mode == 3 and has_bias) else None
+        g_uv = torch.empty_like(uv) if (filter_mode != 0 and need_uv) else None
+        g_uv_da = torch.empty_like(uv_da) if (filter_mode == 3 and has_uv_da and need_da) else None
+        g_bias = torch.empty_like(mip_level_bias) if (filter_mode == 3 and has_bias and need_bias) else None
         g_ptrs = (ctypes.c_void_p * (_TEX_MAX_MIP_LEVEL + 1))()
         g_stack = []
         if enable_mip and has_stack:        # custom mip stack: every level receives its own gradient tensor
@@ -682,7 +686,9 @@ class _texture_func_mip(torch.autograd.Function):
         uv_da = uv_da if ctx.has_uv_da else None
         mip_level_bias = mip_level_bias if ctx.has_bias else None
         filter_mode, mip_wrapper, filter_mode_enum, boundary_mode_enum = ctx.saved_misc
-        g_tex, g_uv, g_uv_da, g_bias, g_stack = _texture_grad(tex, uv, dy, uv_da, mip_level_bias, mip_wrapper, mip_stack, filter_mode_enum, boundary_mode_enum)
+        need = ctx.needs_input_grad
+        g_tex, g_uv, g_uv_da, g_bias, g_stack = _texture_grad(tex, uv, dy, uv_da, mip_level_bias, mip_wrapper, mip_stack, filter_mode_enum, boundary_mode_enum,
+                                                              need_uv=need[2], need_da=need[3], need_bias=need[4])
         if filter_mode == 'linear-mipmap-linear':
             return (None, g_tex, g_uv, g_uv_da, g_bias, None, None, None) + tuple(g_stack)
         return (None, g_tex, g_uv, None, None, None, None, None) + tuple(g_stack)
@@ -700,7 +706,7 @@ class _texture_func(torch.autograd.Function):
     def backward(ctx, dy):
         tex, uv = ctx.saved_tensors
         filter_mode, filter_mode_enum, boundary_mode_enum = ctx.saved_misc
-        g_tex, g_uv, _a, _b, _c = _texture_grad(tex, uv, dy, None, None, None, (), filter_mode_enum, boundary_mode_enum)
+        g_tex, g_uv, _a, _b, _c = _texture_grad(tex, uv, dy, None, None, None, (), filter_mode_enum, boundary_mode_enum, need_uv=ctx.needs_input_grad[2])
         if filter_mode == 'linear':
             return None, g_tex, g_uv, None, None
         return None, g_tex, None, None, None
