@@ -267,25 +267,8 @@ static __device__ __forceinline__ float warp_run_sum(float v, const WarpRuns& r)
     return v;
 }
 
-// Longest run of the warp (warp-uniform): the segmented sums below need ceil(log2(len)) shuffle steps, not always five.
-static __device__ __forceinline__ int warp_max_run(const WarpRuns& r)
-{
-    const int lane = threadIdx.x & 31;
-    return __reduce_max_sync(0xffffffffu, r.is_head ? (r.run_end - lane) : 0);
-}
-// Sum v over each run with only the steps a longest run of `maxlen` lanes needs; valid in the run's head lane.
-static __device__ __forceinline__ float warp_run_sum_n(float v, const WarpRuns& r, int maxlen)
-{
-    const int lane = threadIdx.x & 31;
-    #pragma unroll
-    for (int d = 1; d < 32; d <<= 1)
-    {
-        if (d >= maxlen) break;                         // warp-uniform
-        float t = __shfl_down_sync(0xffffffffu, v, d);
-        if (lane + d < r.run_end) v += t;
-    }
-    return v;
-}
+// (Measured and rejected, profiles/r02_experiments.md: bounding the number of shuffle steps by the warp's longest run --
+// __reduce_max_sync + a warp-uniform early exit -- made every gradient kernel 12-30 % slower than the fixed five steps.)
 
 // ------------------------------------------------------------------------------------------------
 // Block-cooperative staging copies (all streaming kernels run DR_THREADS threads per CTA).

@@ -446,7 +446,6 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const Interp
                 load_row<A>(p.attr + (size_t)vi2 * A, a2);
                 WarpRuns runs = warp_runs(valid ? float_to_triidx(r[u].w) : -1);
                 bool head = runs.is_head && valid;
-                const int maxlen = warp_max_run(runs);
                 float* ga0 = acc + (size_t)(vi0 - voff) * A;
                 float* ga1 = acc + (size_t)(vi1 - voff) * A;
                 float* ga2 = acc + (size_t)(vi2 - voff) * A;
@@ -468,7 +467,7 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const Interp
                         float dv = dsdx * db.z + dsdy * db.w;
                         t0[i] += du; t1[i] += dv; t2[i] += -du - dv;
                     }
-                    t0[i] = warp_run_sum_n(t0[i], runs, maxlen); t1[i] = warp_run_sum_n(t1[i], runs, maxlen); t2[i] = warp_run_sum_n(t2[i], runs, maxlen);
+                    t0[i] = warp_run_sum(t0[i], runs); t1[i] = warp_run_sum(t1[i], runs); t2[i] = warp_run_sum(t2[i], runs);
                 }
                 if (head)
                 {

@@ -928,9 +928,8 @@ __global__ void __launch_bounds__(256, RG_MINB) raster_grad_kernel(const RastGra
             }
             // one atomic per (run of equal triangles, value) instead of one per pixel
             WarpRuns runs = warp_runs(triIdx);
-            const int maxlen = warp_max_run(runs);             // ceil(log2(longest run)) shuffle steps instead of always five
             #pragma unroll
-            for (int i = 0; i < 9; i++) gv[i] = warp_run_sum_n(gv[i], runs, maxlen);
+            for (int i = 0; i < 9; i++) gv[i] = warp_run_sum(gv[i], runs);
             if (runs.is_head && triIdx >= 0)
             {
                 if (p.use_smem)     // shared copy: an fp32 add is a compare-and-swap loop (ATOMS.CAST.SPIN), one per component

@@ -1203,11 +1203,10 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
         }
         const WarpRuns runs = warp_runs2(valid ? triIdx : -1 - lane, n);     // (triangle, image): a group may straddle two images
         const bool head = runs.is_head && valid;
-        const int maxlen = warp_max_run(runs);          // the segmented sums take ceil(log2(longest run)) steps
         if (q.g_attr)                                   // warp-uniform
         {
             #pragma unroll
-            for (int i = 0; i < 2; i++) { t0[i] = warp_run_sum_n(t0[i], runs, maxlen); t1[i] = warp_run_sum_n(t1[i], runs, maxlen); t2[i] = warp_run_sum_n(t2[i], runs, maxlen); }
+            for (int i = 0; i < 2; i++) { t0[i] = warp_run_sum(t0[i], runs); t1[i] = warp_run_sum(t1[i], runs); t2[i] = warp_run_sum(t2[i], runs); }
             if (head)
             {
                 float* ga = q.g_attr + (size_t)aoff * 2;
@@ -1251,7 +1250,7 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
             // same runs as above (key = triangle id and image; attribute and position index buffers may differ, the triangle does
             // not): lanes that were skipped contribute zeros, the head writes when the triangle's position indices are valid
             #pragma unroll
-            for (int i = 0; i < 9; i++) gv9[i] = warp_run_sum_n(gv9[i], runs, maxlen);
+            for (int i = 0; i < 9; i++) gv9[i] = warp_run_sum(gv9[i], runs);
             if (head && !(vi0 < 0 || vi0 >= q.V || vi1 < 0 || vi1 >= q.V || vi2 < 0 || vi2 >= q.V))
             {
                 float* gp = q.g_pos + (size_t)n * q.V * 4;
