@@ -255,24 +255,10 @@ static __device__ __forceinline__ WarpRuns warp_runs2(int key0, int key1)
 }
 
 // Sum v over each run; the result is valid in the run's head lane.
-// RUNSUM_FMA (experiment): the per-step predicate becomes a 0/1 factor folded into an FFMA (SHFL + FFMA instead of SHFL +
-// FADD + FSEL); changes results only when a lane outside the run holds inf / nan.
-#ifndef RUNSUM_FMA
-#define RUNSUM_FMA 0
-#endif
+// (Measured, no gain: folding the per-step predicate into an FFMA with a 0/1 factor -- SHFL + FFMA instead of SHFL + FADD + FSEL.)
 static __device__ __forceinline__ float warp_run_sum(float v, const WarpRuns& r)
 {
     const int lane = threadIdx.x & 31;
-#if RUNSUM_FMA
-    const float m1 = (lane + 1 < r.run_end) ? 1.f : 0.f, m2 = (lane + 2 < r.run_end) ? 1.f : 0.f, m4 = (lane + 4 < r.run_end) ? 1.f : 0.f,
-                m8 = (lane + 8 < r.run_end) ? 1.f : 0.f, m16 = (lane + 16 < r.run_end) ? 1.f : 0.f;
-    v = fmaf(__shfl_down_sync(0xffffffffu, v, 1), m1, v);
-    v = fmaf(__shfl_down_sync(0xffffffffu, v, 2), m2, v);
-    v = fmaf(__shfl_down_sync(0xffffffffu, v, 4), m4, v);
-    v = fmaf(__shfl_down_sync(0xffffffffu, v, 8), m8, v);
-    v = fmaf(__shfl_down_sync(0xffffffffu, v, 16), m16, v);
-    return v;
-#else
     #pragma unroll
     for (int d = 1; d < 32; d <<= 1)
     {
@@ -280,7 +266,6 @@ static __device__ __forceinline__ float warp_run_sum(float v, const WarpRuns& r)
         if (lane + d < r.run_end) v += t;
     }
     return v;
-#endif
 }
 
 // (Measured and rejected, profiles/r02_experiments.md: bounding the number of shuffle steps by the warp's longest run --
