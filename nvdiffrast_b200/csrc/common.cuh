@@ -29,6 +29,26 @@ void b200dr_count_launches(int n);
 // B200: 148 SMs.  Queried once per device at first use.
 int b200dr_num_sms(void);
 
+// Grid size of a persistent, warp-autonomous kernel over the flat pixel array.  A warp visits the 32-pixel groups g, g + S,
+// g + 2S, ... with S = blocks * warps_per_cta.  When S is a multiple of the groups per image row, every warp stays in ONE
+// column of the image for its whole life -- and columns differ a lot in cost (background at the borders, geometry in the
+// middle), so the middle columns' warps set the kernel time while the others idle.  Returns the largest block count <= cap
+// (searching 16 below) whose stride visits as many distinct columns as the CTA shape allows.
+static inline size_t b200dr_balanced_blocks(size_t cap, int warps_per_cta, int W)
+{
+    if (cap <= 1 || W <= 0 || (W & 31)) return cap;            // rows that are not whole groups drift on their own
+    const size_t gpr = (size_t)W / 32;
+    if (gpr <= 1) return cap;
+    size_t best = cap, best_gcd = (size_t)-1;
+    for (size_t b = cap; b > 0 && b + 16 > cap; b--)
+    {
+        size_t x = (b * (size_t)warps_per_cta) % gpr, y = gpr;
+        while (x) { size_t t = y % x; y = x; x = t; }           // y = gcd(stride mod gpr, gpr); stride = 0 gives gpr (pinned)
+        if (y < best_gcd) { best_gcd = y; best = b; }
+    }
+    return best;
+}
+
 #ifdef __CUDACC__
 
 // ------------------------------------------------------------------------------------------------

@@ -2004,7 +2004,7 @@ extern "C" int b200dr_texture_fwd(const float* tex, const float* const* mip_ptrs
         size_t groups = ((size_t)N * H * W + 31) / 32;
         size_t blocks = (groups + (TEX_THREADS / 32) - 1) / (TEX_THREADS / 32);
         size_t bcap = (size_t)b200dr_num_sms() * 12;
-        if (blocks > bcap) blocks = bcap;
+        if (blocks > bcap) blocks = b200dr_balanced_blocks(bcap, TEX_THREADS / 32, W);
         launch_fast_fwd(p, (unsigned)blocks, stream);
         B200DR_CHECK_LAUNCH("texture_fwd()");
         return 0;
@@ -2086,7 +2086,7 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
         size_t per_cta = (TEXG_THREADS / 32) * TEXG_UNROLL;
         size_t blocks = (groups + per_cta - 1) / per_cta;
         size_t bcap = (size_t)b200dr_num_sms() * 20;
-        if (blocks > bcap) blocks = bcap;
+        if (blocks > bcap) blocks = b200dr_balanced_blocks(bcap, TEXG_THREADS / 32, p.tile2d ? W * 4 : W);   // 8x4 tiles: W/8 groups per tile row
         launch_fast_grad(p, (unsigned)blocks, stream);
     }
     else
@@ -2194,7 +2194,7 @@ extern "C" int b200dr_texture_chain_grad(const float* tex, const float* const* m
     size_t groups = ((size_t)N * H * W + 31) / 32;
     size_t blocks = (groups + (TEXG_THREADS / 32) - 1) / (TEXG_THREADS / 32);
     size_t bcap = (size_t)b200dr_num_sms() * TCG_MINB * 4;
-    if (blocks > bcap) blocks = bcap;
+    if (blocks > bcap) blocks = b200dr_balanced_blocks(bcap, TEXG_THREADS / 32, W);
     if (pos) launch_chain_grad<true>(p, q, (unsigned)blocks, stream);
     else     launch_chain_grad<false>(p, q, (unsigned)blocks, stream);
     B200DR_CHECK_LAUNCH(fn);
