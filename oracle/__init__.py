@@ -165,6 +165,23 @@ def antialias_fwd(color, rast, pos, tri):
     return out, items[:n.value].copy()
 
 
+def antialias_knife_pixels(rast, pos, tri, tau=1e-3):
+    """Test support: bool [N,H,W] mask of the pixels that belong to a pixel pair whose antialias analysis sits within `tau` of
+    flipping one of its discrete decisions (silhouette sign tests, axis crossings, candidate choice, |dy| >= |dx|, acceptance
+    window, clamps; see aa_margin in oracle.c).  Only there can two correct fp32 implementations disagree by a finite amount."""
+    rast = _c32(rast); pos = _c32(pos); tri = _ci32(tri)
+    N, H, W = rast.shape[:3]
+    inst = pos.ndim > 2
+    V = pos.shape[1] if inst else pos.shape[0]
+    m = np.empty((N, H, W, 2), np.float32)
+    lib().orc_antialias_margins(_f(rast), _f(pos), _i(tri), N, H, W, V, tri.shape[0], int(inst), _f(m))
+    k = m < tau
+    mask = k[..., 0] | k[..., 1]
+    mask[:, :, 1:] |= k[:, :, :-1, 0]            # right partner of a horizontal pair
+    mask[:, 1:, :] |= k[:, :-1, :, 1]            # upper partner of a vertical pair
+    return mask
+
+
 def antialias_grad(color, rast, pos, tri, dy, items):
     """-> (g_color, g_pos).  torch_antialias.cpp:160-241."""
     color = _c32(color); rast = _c32(rast); pos = _c32(pos); tri = _ci32(tri); dy = _c32(dy); items = _ci32(items)

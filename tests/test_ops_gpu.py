@@ -239,12 +239,18 @@ def test_antialias_vs_oracle(dr, ctx, name, C):
     tpos = cu(pos).requires_grad_(True)
     out = dr.antialias(tcol, rast, tpos, cu(tri))
     oo, items = oracle.antialias_fwd(color, rast_np, pos, tri)
-    assert_close(out.detach().cpu().numpy(), oo, 2e-6, 1e-5, name + " aa out", max_bad_frac=1e-4, hard_atol=1e-3)
+    # pixel pairs whose analysis sits within 1e-3 of flipping a discrete decision (oracle.antialias_knife_pixels) are removed by
+    # predicate; every other pixel is held to the tolerance.  alpha = +-(0.5 - crossing) carries the rounding of the projected
+    # vertex positions (a few 1e-5 px at coordinates of ~1e2 px): abs 1e-4 on the blended colours, 1e-3 |g|_inf on g_pos.
+    knife = oracle.antialias_knife_pixels(rast_np, pos, tri)
+    assert knife.mean() < 1e-3, "the predicate must stay rare (%.3g)" % knife.mean()
+    assert_close(out.detach().cpu().numpy()[~knife], oo[~knife], 1e-4, 1e-5, name + " aa out")
     dy = _rand_like(out.shape, 15)
+    dy[knife] = 0.0                                             # knife-edge pairs then contribute nothing in either implementation
     (out * cu(dy)).sum().backward()
     gc, gp = oracle.antialias_grad(color, rast_np, pos, tri, dy, items)
-    assert_close(tcol.grad.cpu().numpy(), gc, 1e-5, 1e-4, "g_color", max_bad_frac=1e-4)
-    assert_grad_close(tpos.grad.cpu().numpy(), gp, 5e-4, "aa g_pos")
+    assert_close(tcol.grad.cpu().numpy()[~knife], gc[~knife], 1e-4, 1e-4, "g_color")
+    assert_grad_close(tpos.grad.cpu().numpy(), gp, 1e-3, "aa g_pos")
     # precomputed topology gives the same result
     topo = dr.antialias_construct_topology_hash(cu(tri))
     out2 = dr.antialias(cu(color), rast, cu(pos), cu(tri), topology_hash=topo)
@@ -388,7 +394,8 @@ def test_tiny_and_ragged_resolutions(dr, ctx, res):
     color = np.random.default_rng(21).uniform(size=o["rast"].shape[:3] + (3,)).astype(np.float32)
     aa = dr.antialias(cu(color), trast, cu(pos), cu(tri))
     oaa, _ = oracle.antialias_fwd(color, o["rast"], pos, tri)
-    assert_close(aa.cpu().numpy(), oaa, 1e-5, 1e-4, "aa", max_bad_frac=2e-2)
+    knife = oracle.antialias_knife_pixels(o["rast"], pos, tri)
+    assert_close(aa.cpu().numpy()[~knife], oaa[~knife], 1e-4, 1e-4, "aa")
 
 
 @pytest.mark.parametrize("A,diff", [(5, "all"), (12, [0, 11, -2]), (40, None), (40, "all")])
