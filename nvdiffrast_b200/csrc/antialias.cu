@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256) aa_analysis_kernel(const AAParams p)
             const float* c0 = p.color + (size_t)pixel0 * p.C;
             const float* c1 = p.color + (size_t)pixel1 * p.C;
             float* o = p.out + (size_t)(alpha > 0.f ? pixel0 : pixel1) * p.C;
-            for (int i = 0; i < p.C; i++) red_add(o + i, alpha * (__ldg(c1 + i) - __ldg(c0 + i)));
+            for (int i = 0; i < p.C; i++) red_add_global(o + i, alpha * (__ldg(c1 + i) - __ldg(c0 + i)));
 
             unsigned flags = (unsigned)di | ((unsigned)d << AA_FLAG_DOWN_BIT) | ((__float_as_uint(ds) >> 31) << AA_FLAG_TRI1_BIT);
             ((int2*)(p.items + idx))[1] = make_int2((int)flags, __float_as_int(alpha));
@@ -324,8 +324,8 @@ __global__ void __launch_bounds__(256) aa_grad_kernel(const AAParams p)
                 {
                     dd += dy * (__ldg(c1 + i) - __ldg(c0 + i));
                     float v = alpha * dy;
-                    red_add(g0 + i, -v);
-                    red_add(g1 + i, v);
+                    red_add_global(g0 + i, -v);
+                    red_add_global(g1 + i, v);
                 }
             }
             if (dd == 0.f) active = false;
@@ -359,8 +359,8 @@ __global__ void __launch_bounds__(256) aa_grad_kernel(const AAParams p)
             if (runs.is_head && active)
             {
                 float* q1 = p.g_pos + 4 * (size_t)vi1; float* q2 = p.g_pos + 4 * (size_t)vi2;
-                red_add(q1 + 0, g[0]); red_add(q1 + 1, g[1]); red_add(q1 + 3, g[2]);
-                red_add(q2 + 0, g[3]); red_add(q2 + 1, g[4]); red_add(q2 + 3, g[5]);
+                red_add_global(q1 + 0, g[0]); red_add_global(q1 + 1, g[1]); red_add_global(q1 + 3, g[2]);
+                red_add_global(q2 + 0, g[3]); red_add_global(q2 + 1, g[4]); red_add_global(q2 + 3, g[5]);
             }
         }
     }

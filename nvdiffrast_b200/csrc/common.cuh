@@ -356,8 +356,19 @@ static __device__ __forceinline__ float warp_run_sum_max4(float v, const WarpRun
     return v;
 }
 
-// fp32 add without return value (RED).  Works on shared and global addresses.
+// fp32 add without return value (RED).  Works on shared and global addresses (generic pointer: the compiler emits an address
+// space query and both code paths -- use the two below where the space is known).
 static __device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
+// global memory only: REDG.E.ADD.F32, fire and forget
+static __device__ __forceinline__ void red_add_global(float* p, float v)
+{
+    asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+// shared memory only (fp32 adds to shared memory are compare-and-swap loops, ATOMS.CAST.SPIN; no address-space query here)
+static __device__ __forceinline__ void red_add_shared(float* p, float v)
+{
+    asm volatile("red.shared.add.f32 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v) : "memory");
+}
 // 128-bit vector reduction (global memory only, 16-byte aligned): REDG.E.ADD.F32x4 on sm_100a.
 static __device__ __forceinline__ void red_add4(float* p, float4 v)
 {

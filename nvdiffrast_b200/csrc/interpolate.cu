@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_kernel(const Inte
         for (int i = tid; i < acc_n; i += IP_THREADS)
         {
             float v = s_acc[i];
-            if (v != 0.f) red_add(gbase + i, v);
+            if (v != 0.f) red_add_global(gbase + i, v);
         }
     }
 }
@@ -487,10 +487,15 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const Interp
                         // 12-byte rows: the 8-byte aligned pair is (0,1) for even vertices and (1,2) for odd ones
                         red_add3(ga0, t0[0], t0[1 % A], t0[2 % A]); red_add3(ga1, t1[0], t1[1 % A], t1[2 % A]); red_add3(ga2, t2[0], t2[1 % A], t2[2 % A]);
                     }
+                    else if (p.use_smem_acc)
+                    {
+                        #pragma unroll
+                        for (int i = 0; i < A; i++) { red_add_shared(ga0 + i, t0[i]); red_add_shared(ga1 + i, t1[i]); red_add_shared(ga2 + i, t2[i]); }
+                    }
                     else
                     {
                         #pragma unroll
-                        for (int i = 0; i < A; i++) { red_add(ga0 + i, t0[i]); red_add(ga1 + i, t1[i]); red_add(ga2 + i, t2[i]); }
+                        for (int i = 0; i < A; i++) { red_add_global(ga0 + i, t0[i]); red_add_global(ga1 + i, t1[i]); red_add_global(ga2 + i, t2[i]); }
                     }
                 }
                 if (!valid) { gr = make_float4(0.f, 0.f, 0.f, 0.f); gdb = gr; }
@@ -509,7 +514,7 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const Interp
         for (int i = tid; i < acc_n; i += IP_THREADS)
         {
             float v = s_acc[i];
-            if (v != 0.f) red_add(gbase + i, v);
+            if (v != 0.f) red_add_global(gbase + i, v);
         }
     }
 }

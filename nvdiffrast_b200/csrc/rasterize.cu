@@ -934,9 +934,9 @@ __global__ void __launch_bounds__(256, RG_MINB) raster_grad_kernel(const RastGra
             {
                 if (p.use_smem)     // shared copy: an fp32 add is a compare-and-swap loop (ATOMS.CAST.SPIN), one per component
                 {
-                    red_add(acc + 4 * vi0 + 0, gv[0]); red_add(acc + 4 * vi0 + 1, gv[1]); red_add(acc + 4 * vi0 + 3, gv[2]);
-                    red_add(acc + 4 * vi1 + 0, gv[3]); red_add(acc + 4 * vi1 + 1, gv[4]); red_add(acc + 4 * vi1 + 3, gv[5]);
-                    red_add(acc + 4 * vi2 + 0, gv[6]); red_add(acc + 4 * vi2 + 1, gv[7]); red_add(acc + 4 * vi2 + 3, gv[8]);
+                    red_add_shared(acc + 4 * vi0 + 0, gv[0]); red_add_shared(acc + 4 * vi0 + 1, gv[1]); red_add_shared(acc + 4 * vi0 + 3, gv[2]);
+                    red_add_shared(acc + 4 * vi1 + 0, gv[3]); red_add_shared(acc + 4 * vi1 + 1, gv[4]); red_add_shared(acc + 4 * vi1 + 3, gv[5]);
+                    red_add_shared(acc + 4 * vi2 + 0, gv[6]); red_add_shared(acc + 4 * vi2 + 1, gv[7]); red_add_shared(acc + 4 * vi2 + 3, gv[8]);
                 }
                 else                // global: one 128-bit vector reduction per vertex (z receives +0)
                 {
@@ -954,7 +954,7 @@ __global__ void __launch_bounds__(256, RG_MINB) raster_grad_kernel(const RastGra
         for (int i = tid; i < p.V * 4; i += 256)
         {
             float v = s_acc[i];
-            if (v != 0.f) red_add(gbase + i, v);
+            if (v != 0.f) red_add_global(gbase + i, v);
         }
     }
 }
