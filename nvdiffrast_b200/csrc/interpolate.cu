@@ -366,8 +366,11 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_fwd_fast(const InterpP
     }
 }
 
+#ifndef IPG_MINB
+#define IPG_MINB 1
+#endif
 template <int A, bool DA>
-__global__ void __launch_bounds__(IP_THREADS) interpolate_grad_fast(const InterpParams p)
+__global__ void __launch_bounds__(IP_THREADS, IPG_MINB) interpolate_grad_fast(const InterpParams p)
 {
     extern __shared__ __align__(16) float s_dyn[];
     constexpr int SK = (A == 3) ? (DA ? 6 : 3) : 1;
