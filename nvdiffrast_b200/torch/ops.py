@@ -444,6 +444,28 @@ class _interpolate_func(torch.autograd.Function):
         return g_attr, g_rast, None
 
 
+def _diff_attr_arg(diff_attrs):
+    """`diff_attrs` of interpolate(): None | 'all' | 1-D sequence of attribute indices  ->  (all?, [indices])
+    (same accepted forms as nvdiffrast/torch/ops.py:276-284)."""
+    if isinstance(diff_attrs, str):
+        assert diff_attrs == 'all', "diff_attrs: a list of attribute indices or 'all'"
+        return True, []
+    if diff_attrs is None:
+        return False, []
+    idx = np.asarray(diff_attrs, np.int32)
+    assert idx.ndim == 1, "diff_attrs must be one-dimensional"
+    return False, idx.tolist()
+
+
+def _mip_limit(max_mip_level):
+    """None -> -1 (no limit); otherwise a non-negative int."""
+    if max_mip_level is None:
+        return -1
+    level = int(max_mip_level)
+    assert level >= 0, "max_mip_level must be >= 0"
+    return level
+
+
 def interpolate(attr, rast, tri, rast_db=None, diff_attrs=None):
     """Interpolate vertex attributes.
 
@@ -459,20 +481,13 @@ def interpolate(attr, rast, tri, rast_db=None, diff_attrs=None):
         (out, out_da): [minibatch_size, height, width, num_attributes] and
         [minibatch_size, height, width, 2 * len(diff_attrs)] ((dA/dX, dA/dY) pairs; last dimension 0 if unused).
     """
-    if diff_attrs is None:
-        diff_attrs = []
-    elif diff_attrs != 'all':
-        diff_attrs = np.asarray(diff_attrs, np.int32)
-        assert len(diff_attrs.shape) == 1
-        diff_attrs = diff_attrs.tolist()
-    diff_attrs_all = int(diff_attrs == 'all')
-    diff_attrs_list = [] if diff_attrs_all else diff_attrs
-
-    assert all(isinstance(x, torch.Tensor) for x in (attr, rast, tri))
-    if diff_attrs:
-        assert isinstance(rast_db, torch.Tensor)
-        out = _interpolate_func_da.apply(attr, rast, tri, rast_db, diff_attrs_all, diff_attrs_list)
-        _Provenance("interpolate", (attr, rast, tri, rast_db), out, diff_all=bool(diff_attrs_all))
+    want_all, which = _diff_attr_arg(diff_attrs)
+    for name, t in (("attr", attr), ("rast", rast), ("tri", tri)):
+        assert isinstance(t, torch.Tensor), "%s must be a tensor" % name
+    if want_all or which:
+        assert isinstance(rast_db, torch.Tensor), "diff_attrs needs rast_db"
+        out = _interpolate_func_da.apply(attr, rast, tri, rast_db, int(want_all), which)
+        _Provenance("interpolate", (attr, rast, tri, rast_db), out, diff_all=want_all)
         return out
     out = _interpolate_func.apply(attr, rast, tri)
     _Provenance("interpolate", (attr, rast, tri, None), out, diff_all=False)
@@ -818,38 +833,33 @@ def texture(tex, uv, uv_da=None, mip_level_bias=None, mip=None, filter_mode='aut
         mip_level_bias: (optional) per-pixel mip level bias [minibatch_size, height, width].
         mip: (optional) result of `texture_construct_mip()` or a list of tensors forming a custom mip stack.
         filter_mode: 'auto', 'nearest', 'linear', 'linear-mipmap-nearest', 'linear-mipmap-linear'.
-        boundary_mode: 'wrap', 'clamp', 'zero', 'cube' (cube maps: up to 4 channels in this build).
+        boundary_mode: 'wrap', 'clamp', 'zero', 'cube'.
         max_mip_level: limits the number of mip levels built / used.
 
     Returns:
         [minibatch_size, height, width, tex_channels].
     """
-    if filter_mode == 'auto':
-        filter_mode = 'linear-mipmap-linear' if (uv_da is not None or mip_level_bias is not None) else 'linear'
-    if max_mip_level is None:
-        max_mip_level = -1
-    else:
-        max_mip_level = int(max_mip_level)
-        assert max_mip_level >= 0
-    assert isinstance(tex, torch.Tensor) and isinstance(uv, torch.Tensor)
+    for name, t in (("tex", tex), ("uv", uv)):
+        assert isinstance(t, torch.Tensor), "%s must be a tensor" % name
+    max_mip_level = _mip_limit(max_mip_level)
+    has_footprint = uv_da is not None or mip_level_bias is not None
+    if filter_mode == 'auto':                                   # mip-mapped exactly when a footprint was given
+        filter_mode = 'linear-mipmap-linear' if has_footprint else 'linear'
     if 'mipmap' in filter_mode:
-        assert isinstance(uv_da, torch.Tensor) or isinstance(mip_level_bias, torch.Tensor)
-    if max_mip_level == 0 and filter_mode in ['linear-mipmap-nearest', 'linear-mipmap-linear']:
-        filter_mode = 'linear'
-    filter_mode_enum = _FILTER_MODES[filter_mode]
-    boundary_mode_enum = _BOUNDARY_MODES[boundary_mode]
+        assert isinstance(uv_da, torch.Tensor) or isinstance(mip_level_bias, torch.Tensor), "mip-mapped filtering needs uv_da or mip_level_bias"
+        if max_mip_level == 0 and filter_mode.startswith('linear-'):
+            filter_mode = 'linear'                              # only the base level may be used
+    filter_mode_enum, boundary_mode_enum = _FILTER_MODES[filter_mode], _BOUNDARY_MODES[boundary_mode]
 
     mip_wrapper, mip_stack = None, []
     if 'mipmap' in filter_mode:
-        if mip is not None:
-            assert isinstance(mip, (TextureMipWrapper, list))
-            if isinstance(mip, list):
-                assert all(isinstance(x, torch.Tensor) for x in mip)
-                mip_stack = mip
-            else:
-                mip_wrapper = mip
-        else:
+        if mip is None:
             mip_wrapper = _texture_construct_mip(tex, max_mip_level, boundary_mode == 'cube')
+        elif isinstance(mip, TextureMipWrapper):
+            mip_wrapper = mip
+        else:
+            assert isinstance(mip, list) and all(isinstance(x, torch.Tensor) for x in mip), "mip: texture_construct_mip() result or a list of tensors"
+            mip_stack = mip
     plan = _fusion_plan(tex, uv, uv_da if 'mipmap' in filter_mode else None, mip_level_bias, mip_stack, filter_mode, boundary_mode)
     if plan is not None:
         # the intermediates enter as constants (detached): the fused node owns the whole path colour -> (tex, attr, pos)
@@ -865,14 +875,9 @@ def texture(tex, uv, uv_da=None, mip_level_bias=None, mip=None, filter_mode='aut
 
 def texture_construct_mip(tex, max_mip_level=None, cube_mode=False):
     """Construct a mipmap stack for a texture that stays constant (pass the result as `mip` to `texture()`)."""
-    assert isinstance(tex, torch.Tensor)
-    assert cube_mode is True or cube_mode is False
-    if max_mip_level is None:
-        max_mip_level = -1
-    else:
-        max_mip_level = int(max_mip_level)
-        assert max_mip_level >= 0
-    return _texture_construct_mip(tex, max_mip_level, cube_mode)
+    assert isinstance(tex, torch.Tensor), "tex must be a tensor"
+    assert isinstance(cube_mode, bool)
+    return _texture_construct_mip(tex, _mip_limit(max_mip_level), cube_mode)
 
 
 # ----------------------------------------------------------------------------------------------
