@@ -269,8 +269,19 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_kernel(const Inte
 #ifndef IPF_UNROLL_DA
 #define IPF_UNROLL_DA 2
 #endif
-#ifndef IPG_UNROLL
-#define IPG_UNROLL 2        // backward: 2 (4: 0.783 -> 0.862 ms, registers spill; 1: 0.835)
+// backward (r02 call 13): without differentials 4 groups in flight at <= 64 registers (4 CTAs/SM): A = 3 target 0.710 -> 0.677 ms,
+// c2 0.509 -> 0.482; with differentials the same setting loses (c3 op-by-op 0.789 -> 0.808), it keeps 2 groups, unconstrained
+#ifndef IPG_UNROLL_PLAIN
+#define IPG_UNROLL_PLAIN 4
+#endif
+#ifndef IPG_UNROLL_DA
+#define IPG_UNROLL_DA 2
+#endif
+#ifndef IPG_MINB_PLAIN
+#define IPG_MINB_PLAIN 4
+#endif
+#ifndef IPG_MINB_DA
+#define IPG_MINB_DA 1
 #endif
 
 template <int A>
@@ -366,12 +377,10 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_fwd_fast(const InterpP
     }
 }
 
-#ifndef IPG_MINB
-#define IPG_MINB 1
-#endif
 template <int A, bool DA>
-__global__ void __launch_bounds__(IP_THREADS, IPG_MINB) interpolate_grad_fast(const InterpParams p)
+__global__ void __launch_bounds__(IP_THREADS, DA ? IPG_MINB_DA : IPG_MINB_PLAIN) interpolate_grad_fast(const InterpParams p)
 {
+    constexpr int IPG_UNROLL = DA ? IPG_UNROLL_DA : IPG_UNROLL_PLAIN;
     extern __shared__ __align__(16) float s_dyn[];
     constexpr int SK = (A == 3) ? (DA ? 6 : 3) : 1;
     float* s_stage = s_dyn;                                             // [8 warps][32 * SK]
@@ -653,7 +662,8 @@ extern "C" int b200dr_interpolate_grad(const float* attr, const float* rast, con
         p.use_smem_acc = (acc_b + stage_b <= 64 * 1024 && V <= ACC_SMEM_MAX_V) ? 1 : 0;
         size_t smem_f = stage_b + (p.use_smem_acc ? acc_b : 0);
         int groups = (int)(((size_t)H * W + 31) / 32);
-        int gx = (groups + (IP_THREADS / 32) * IPG_UNROLL - 1) / ((IP_THREADS / 32) * IPG_UNROLL);
+        const int unroll = da ? IPG_UNROLL_DA : IPG_UNROLL_PLAIN;
+        int gx = (groups + (IP_THREADS / 32) * unroll - 1) / ((IP_THREADS / 32) * unroll);
         if (smem_f > 48 * 1024)
         {
             switch (A * 2 + (da ? 1 : 0)) {
