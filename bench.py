@@ -132,8 +132,22 @@ def op_bytes(workload, P, A, D, C):
         # fused texture -> interpolate -> rasterize backward: dy + rast + rast_db in, nothing per-pixel out (the three ops it
         # replaces move (16+4C+32) + (32+4A+32+8D) + 48 = 196 B/px through their tensor boundaries)
         "b200dr_texture_chain_grad": (4 * C + 32) * P,
+        # fused interpolate -> rasterize backward: rast + dy (+ rast_db + dda) in, nothing per-pixel out
+        "b200dr_interpolate_chain_grad": (16 + 4 * A + (16 + 8 * D if D else 0)) * P,
     }
     return b
+
+
+def replaced_bytes(nbytes):
+    """Bytes the op-by-op kernels move through their tensor boundaries for the work of each fused backward op."""
+    ig, rg = nbytes["b200dr_interpolate_grad"], nbytes["b200dr_rasterize_grad"]
+    return {"b200dr_texture_chain_grad": nbytes["b200dr_texture_grad"] + ig + rg, "b200dr_interpolate_chain_grad": ig + rg}
+
+
+def op_by_op_bytes(nbytes, ops, K_total):
+    """Algorithmic bytes per step counted at the reference's op boundaries (fused ops replaced by what they stand for)."""
+    rep = replaced_bytes(nbytes)
+    return sum((rep.get(n, nbytes.get(n, 0))) * ops[n][1] / K_total for n in ops if n in nbytes)
 
 
 class Pipeline:
@@ -424,10 +438,21 @@ def side_config(mod, name, K, W, device, peak):
     nbytes = op_bytes("c3" if pipe.full else name, P, A, D, C)
     table, ops = ops_table(r["trace"], K * r["rounds"], nbytes, peak)
     chain = sum(nbytes[n] * ops[n][1] / (K * r["rounds"]) for n in ops if n in nbytes)
+    api = op_by_op_bytes(nbytes, ops, K * r["rounds"])
     out = {"workload": WORKLOAD_TEXT[name] % (res, n_img), "ms_per_step": r["ms_per_step"], "value": P / (r["ms_per_step"] * 1e-3) / 1e6,
            "unit": "Mpixel/s", "steps": K, "timed_rounds": r["rounds"], "clocks": r["clocks"],
            "ops": {k: {"ms": v["ms"], "frac": v.get("frac")} for k, v in table.items()},
-           "chain_roofline": {"algorithmic_bytes_per_step": chain, "frac": chain / (r["ms_per_step"] * 1e-3) / 1e9 / peak}}
+           "chain_roofline": {"algorithmic_bytes_per_step": chain, "frac": chain / (r["ms_per_step"] * 1e-3) / 1e9 / peak,
+                              "op_by_op_bytes_per_step": api, "effective_frac_vs_op_by_op_bytes": api / (r["ms_per_step"] * 1e-3) / 1e9 / peak}}
+    if any(n in ops for n in replaced_bytes(nbytes)):
+        # the same chain with the fused backward nodes switched off (B200DR_FUSION=0), same inputs, same box
+        mod.set_fusion(False)
+        try:
+            ru = timed_run(pipe, K, 1, 1, 0, device.index or 0, device, "ours", 0.5)
+        finally:
+            mod.set_fusion(True)
+        tu, _ = ops_table(ru["trace"], K * ru["rounds"], nbytes, peak)
+        out["ops_unfused"] = {"ms_per_step": ru["ms_per_step"], "ops": {k: {"ms": v["ms"], "frac": v.get("frac")} for k, v in tu.items()}}
     del pipe
     torch.cuda.empty_cache()
     return out
@@ -632,13 +657,15 @@ def main():
         chain_bytes = sum(nbytes[n] * ops[n][1] / Kt for n in ops if n in nbytes)
         out["chain_roofline"] = {"algorithmic_bytes_per_step": chain_bytes, "achieved_GBps": chain_bytes / (ms_step * 1e-3) / 1e9,
                                  "frac": chain_bytes / (ms_step * 1e-3) / 1e9 / peak}
-        fused = "b200dr_texture_chain_grad" in ops
+        fused = any(n in ops for n in replaced_bytes(nbytes))
         out["fusion"] = {"enabled": bool(mod.get_fusion()), "chain_backward_fused": fused,
-                         "note": "texture+interpolate+rasterize backward run as ONE kernel that keeps g_uv/g_uv_da/g_rast/g_rast_db in registers: "
-                                 "it moves 44 of the 196 B/px the three reference ops move and is bound by instruction issue, not HBM; "
+                         "note": ("texture+interpolate+rasterize backward run as ONE kernel that keeps g_uv/g_uv_da/g_rast/g_rast_db in registers: "
+                                  "it moves 44 of the 196 B/px the three reference ops move and is bound by instruction issue, not HBM; "
+                                  if full else
+                                  "interpolate+rasterize backward run as ONE kernel that keeps g_rast in registers: 28 of 76 B/px; ") +
                                  "`ops_unfused` times the op-by-op path (B200DR_FUSION=0) on the same inputs" if fused else None}
         if fused:
-            api_bytes = sum(v * ops[n][1] / Kt for n, v in nbytes.items() if n in ops and n != "b200dr_texture_chain_grad") + 196 * P
+            api_bytes = op_by_op_bytes(nbytes, ops, Kt)
             out["chain_roofline"]["op_by_op_bytes_per_step"] = api_bytes
             out["chain_roofline"]["effective_frac_vs_op_by_op_bytes"] = api_bytes / (ms_step * 1e-3) / 1e9 / peak
         if fused and world == 1 and not args.no_extras:

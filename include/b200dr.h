@@ -186,6 +186,19 @@ int b200dr_texture_chain_grad(const float* tex, const float* const* mip_ptrs, in
                               float* g_tex, float* g_attr, float* g_rast, float* g_rast_db, float* g_pos,
                               void* scratch, size_t scratch_bytes, void* stream);
 
+/* EXTENSION (same status as b200dr_texture_chain_grad): the backward of interpolate(attr, rasterize(pos)) in ONE pass.
+ * Equivalent to interpolate_grad[_da] (torch_interpolate.cpp:137-248) followed by rasterize_grad[_db]
+ * (torch_rasterize.cpp:171-262) without the g_rast / g_rast_db round trip: 28 instead of 76 bytes per pixel for three plain
+ * attributes.  Preconditions the caller guarantees: rast (and rast_db) are rasterize's outputs for pos [N,Vp,4] / pos_tri [T,3]
+ * (instanced mode); 1 <= A <= 4; differentials for all attributes (diff_all = 1: rast_db, dda required) or none (diff_all = 0).
+ * attr / tri / attr_bc / instance_mode as in b200dr_interpolate_grad.  grad_db: rasterize() was called with grad_db=True.
+ * g_attr (shape of attr) and g_pos [N,Vp,4] MUST be zero-filled by the caller; both are accumulated into. */
+int b200dr_interpolate_chain_grad(const float* attr, const float* rast, const int32_t* tri, const float* dy,
+                                  const float* rast_db, const float* dda,
+                                  const float* pos, const int32_t* pos_tri, int Vp, int grad_db,
+                                  int N, int H, int W, int V, int T, int A, int attr_bc, int instance_mode, int diff_all,
+                                  float* g_attr, float* g_pos, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

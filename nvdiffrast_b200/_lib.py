@@ -36,6 +36,7 @@ SIGNATURES = {
     "b200dr_texture_grad_scratch_bytes": (_sz, [_int, _int, _int, _int, _int]),
     "b200dr_texture_chain_grad": (_int, [_vp, _c.POINTER(_vp), _int, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _int, _int] + [_int] * 10 +
                                   [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "b200dr_interpolate_chain_grad": (_int, [_vp] * 8 + [_int] * 11 + [_vp, _vp, _vp]),
     "b200dr_texture_grad": (_int, [_vp, _c.POINTER(_vp), _int, _vp, _vp, _vp, _vp] + [_int] * 9 + [_vp, _c.POINTER(_vp), _int, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 

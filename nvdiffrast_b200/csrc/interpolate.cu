@@ -9,6 +9,7 @@
 // triangle ids inside the warp (5 shuffles), accumulated in a per-CTA shared-memory copy of the gradient tensor when
 // it fits, and flushed with one atomic per touched element per CTA.
 #include "common.cuh"
+#include "pixel_math.cuh"
 
 namespace {
 
@@ -24,6 +25,11 @@ struct InterpParams
     int staged;             // 1: per-pixel channel tensors go through shared-memory staging
     int use_smem_acc;       // backward: 1 = accumulate g_attr in shared memory
     int chunks;             // 256-pixel chunks per image
+    // fused backward through rasterize (interpolate_grad_fast<.., RASTER = true>): g_rast / g_rast_db stay in registers and go
+    // straight through the rasterizer's pixel math into g_pos
+    const float* pos; const int32_t* pos_tri; float* g_pos;    // [N,Vp,4]; [T,3]; [N,Vp,4] zero-initialised
+    int Vp, grad_db, use_smem_pos;
+    float xs, xo, ys, yo;   // pixel centre -> clip space: fx = xs * X + xo
     int diff[IP_MAX_DIFF];
 };
 
@@ -269,19 +275,19 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_kernel(const Inte
 #ifndef IPF_UNROLL_DA
 #define IPF_UNROLL_DA 2
 #endif
-// backward (r02 call 13): without differentials 4 groups in flight at <= 64 registers (4 CTAs/SM): A = 3 target 0.710 -> 0.677 ms,
-// c2 0.509 -> 0.482; with differentials the same setting loses (c3 op-by-op 0.789 -> 0.808), it keeps 2 groups, unconstrained
+// backward (r02 call 13, same box): 4 groups in flight at <= 64 registers (4 CTAs/SM) against 2 groups unconstrained: A = 3 target
+// 0.710 -> 0.677 ms, c2 0.509 -> 0.482, c3 op-by-op (A = 2 + differentials) 0.846 -> 0.808; 3 groups: 0.690 / 0.487 / 0.817
 #ifndef IPG_UNROLL_PLAIN
 #define IPG_UNROLL_PLAIN 4
 #endif
 #ifndef IPG_UNROLL_DA
-#define IPG_UNROLL_DA 2
+#define IPG_UNROLL_DA 4
 #endif
 #ifndef IPG_MINB_PLAIN
 #define IPG_MINB_PLAIN 4
 #endif
 #ifndef IPG_MINB_DA
-#define IPG_MINB_DA 1
+#define IPG_MINB_DA 4
 #endif
 
 template <int A>
@@ -377,14 +383,21 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_fwd_fast(const InterpP
     }
 }
 
-template <int A, bool DA>
-__global__ void __launch_bounds__(IP_THREADS, DA ? IPG_MINB_DA : IPG_MINB_PLAIN) interpolate_grad_fast(const InterpParams p)
+// RASTER: the rasterizer's backward is applied in the same pass (b200dr_interpolate_chain_grad): per pixel, (g_rast.xy, g_rast_db)
+// go through pm::raster_grad instead of memory, and the vertex-position gradients are summed over the same triangle runs.
+#ifndef IPC_MINB
+#define IPC_MINB 3
+#endif
+#define IPC_SMEM_MAX_VP 1024    // position gradients of one image in shared memory up to this many vertices (as raster_grad_kernel)
+template <int A, bool DA, bool RASTER>
+__global__ void __launch_bounds__(IP_THREADS, RASTER ? IPC_MINB : (DA ? IPG_MINB_DA : IPG_MINB_PLAIN)) interpolate_grad_fast(const InterpParams p)
 {
     constexpr int IPG_UNROLL = DA ? IPG_UNROLL_DA : IPG_UNROLL_PLAIN;
     extern __shared__ __align__(16) float s_dyn[];
     constexpr int SK = (A == 3) ? (DA ? 6 : 3) : 1;
     float* s_stage = s_dyn;                                             // [8 warps][32 * SK]
     float* s_acc = s_dyn + (IP_THREADS / 32) * 32 * SK;                 // [V * A] when use_smem_acc
+    float* s_pos = s_acc + (p.use_smem_acc ? p.V * A : 0);              // RASTER: [Vp * 4] when use_smem_pos (this image's g_pos)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.y;
     const int hw = p.H * p.W;
@@ -400,10 +413,10 @@ __global__ void __launch_bounds__(IP_THREADS, DA ? IPG_MINB_DA : IPG_MINB_PLAIN)
     float* sw = s_stage + warp * 32 * SK;
 
     if (p.use_smem_acc)
-    {
         for (int i = tid; i < acc_n; i += IP_THREADS) s_acc[i] = 0.f;
-        __syncthreads();
-    }
+    if (RASTER && p.use_smem_pos)
+        for (int i = tid; i < p.Vp * 4; i += IP_THREADS) s_pos[i] = 0.f;
+    if (p.use_smem_acc || (RASTER && p.use_smem_pos)) __syncthreads();
 
     for (int g0 = blockIdx.x * (IP_THREADS / 32) + warp; g0 < groups; g0 += IPG_UNROLL * wstride)
     {
@@ -511,8 +524,56 @@ __global__ void __launch_bounds__(IP_THREADS, DA ? IPG_MINB_DA : IPG_MINB_PLAIN)
                     }
                 }
                 if (!valid) { gr = make_float4(0.f, 0.f, 0.f, 0.f); gdb = gr; }
+                if (RASTER)
+                {
+                    // rasterize backward on the pixel's own (g_rast.xy, g_rast_db): csrc/common/rasterize.cu:119-273 as restated in
+                    // pixel_math.cuh.  The runs are the attribute runs (same triangle id); position indices come from rasterize's tri.
+                    int pi0 = 0, pi1 = 0, pi2 = 0;
+                    if (valid)
+                    {
+                        const int32_t* pt = p.pos_tri + (size_t)(float_to_triidx(r[u].w) - 1) * 3;
+                        pi0 = __ldg(pt); pi1 = __ldg(pt + 1); pi2 = __ldg(pt + 2);
+                    }
+                    const bool pidx_ok = valid && !(pi0 < 0 || pi0 >= p.Vp || pi1 < 0 || pi1 >= p.Vp || pi2 < 0 || pi2 >= p.Vp);
+                    // pixels whose incoming gradients are all +-0 are skipped (csrc/common/rasterize.cu:143-148)
+                    const unsigned nz_dy = (__float_as_uint(gr.x) | __float_as_uint(gr.y)) << 1;
+                    const unsigned nz_db = (DA && p.grad_db) ? ((__float_as_uint(gdb.x) | __float_as_uint(gdb.y) | __float_as_uint(gdb.z) | __float_as_uint(gdb.w)) << 1) : 0u;
+                    float gv9[9];
+                    #pragma unroll
+                    for (int i = 0; i < 9; i++) gv9[i] = 0.f;
+                    if (pidx_ok && (nz_dy | nz_db) != 0u)
+                    {
+                        const float4* vb = (const float4*)p.pos + (size_t)n * p.Vp;
+                        const unsigned py = (unsigned)px / (unsigned)p.W, pxx = (unsigned)px - py * (unsigned)p.W;
+                        const float fx = p.xs * (float)pxx + p.xo, fy = p.ys * (float)py + p.yo;
+                        pm::PixelTri t;
+                        pm::pixel_tri(t, __ldg(vb + pi0), __ldg(vb + pi1), __ldg(vb + pi2), fx, fy);
+                        float gx[3], gy[3], gw[3];
+                        pm::raster_grad<DA>(t, fx, fy, p.xs, p.ys, gr.x, gr.y, gdb, nz_db != 0u, gx, gy, gw);
+                        #pragma unroll
+                        for (int k = 0; k < 3; k++) { gv9[3 * k] = gx[k]; gv9[3 * k + 1] = gy[k]; gv9[3 * k + 2] = gw[k]; }
+                    }
+                    #pragma unroll
+                    for (int i = 0; i < 9; i++) gv9[i] = warp_run_sum(gv9[i], runs);
+                    if (head && pidx_ok)
+                    {
+                        if (p.use_smem_pos)
+                        {
+                            red_add_shared(s_pos + 4 * pi0, gv9[0]); red_add_shared(s_pos + 4 * pi0 + 1, gv9[1]); red_add_shared(s_pos + 4 * pi0 + 3, gv9[2]);
+                            red_add_shared(s_pos + 4 * pi1, gv9[3]); red_add_shared(s_pos + 4 * pi1 + 1, gv9[4]); red_add_shared(s_pos + 4 * pi1 + 3, gv9[5]);
+                            red_add_shared(s_pos + 4 * pi2, gv9[6]); red_add_shared(s_pos + 4 * pi2 + 1, gv9[7]); red_add_shared(s_pos + 4 * pi2 + 3, gv9[8]);
+                        }
+                        else
+                        {
+                            float* gp = p.g_pos + (size_t)n * p.Vp * 4;
+                            red_add4(gp + 4 * pi0, make_float4(gv9[0], gv9[1], 0.f, gv9[2]));
+                            red_add4(gp + 4 * pi1, make_float4(gv9[3], gv9[4], 0.f, gv9[5]));
+                            red_add4(gp + 4 * pi2, make_float4(gv9[6], gv9[7], 0.f, gv9[8]));
+                        }
+                    }
+                }
             }
-            if (inb[u])
+            if (!RASTER && inb[u])
             {
                 st_stream_f4((float4*)p.g_rast + img + px, gr);
                 if (DA) st_stream_f4((float4*)p.g_rast_db + img + px, gdb);
@@ -520,13 +581,22 @@ __global__ void __launch_bounds__(IP_THREADS, DA ? IPG_MINB_DA : IPG_MINB_PLAIN)
         }
     }
 
+    if (p.use_smem_acc || (RASTER && p.use_smem_pos)) __syncthreads();
     if (p.use_smem_acc)
     {
-        __syncthreads();
         for (int i = tid; i < acc_n; i += IP_THREADS)
         {
             float v = s_acc[i];
             if (v != 0.f) red_add_global(gbase + i, v);
+        }
+    }
+    if (RASTER && p.use_smem_pos)
+    {
+        float* gp = p.g_pos + (size_t)n * p.Vp * 4;
+        for (int i = tid; i < p.Vp * 4; i += IP_THREADS)
+        {
+            float v = s_pos[i];
+            if (v != 0.f) red_add_global(gp + i, v);
         }
     }
 }
@@ -555,21 +625,52 @@ static bool fast_ok(const InterpParams& p, bool da, const void* attr)
         case 9: KERNEL<4, true ><<<GRID, IP_THREADS, SMEM, STREAM>>>(P); break;             \
         } } while (0)
 
-// resident CTAs per SM of the fast backward kernel for this (A, DA, dynamic smem): sizes the persistent grid
-static int grad_fast_resident(int A, bool da, size_t smem)
+typedef void (*IpgKernel)(const InterpParams);
+// the backward kernel for (A, differentials, fused rasterize backward)
+static IpgKernel grad_fast_kernel(int A, bool da, bool raster)
 {
-    int n = 0;
-    switch (A * 2 + (da ? 1 : 0)) {
-    case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<1, false>, IP_THREADS, smem); break;
-    case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<1, true >, IP_THREADS, smem); break;
-    case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<2, false>, IP_THREADS, smem); break;
-    case 5: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<2, true >, IP_THREADS, smem); break;
-    case 6: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<3, false>, IP_THREADS, smem); break;
-    case 7: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<3, true >, IP_THREADS, smem); break;
-    case 8: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<4, false>, IP_THREADS, smem); break;
-    case 9: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, interpolate_grad_fast<4, true >, IP_THREADS, smem); break;
+    switch (A * 4 + (da ? 2 : 0) + (raster ? 1 : 0)) {
+    case  4: return interpolate_grad_fast<1, false, false>;  case  5: return interpolate_grad_fast<1, false, true>;
+    case  6: return interpolate_grad_fast<1, true,  false>;  case  7: return interpolate_grad_fast<1, true,  true>;
+    case  8: return interpolate_grad_fast<2, false, false>;  case  9: return interpolate_grad_fast<2, false, true>;
+    case 10: return interpolate_grad_fast<2, true,  false>;  case 11: return interpolate_grad_fast<2, true,  true>;
+    case 12: return interpolate_grad_fast<3, false, false>;  case 13: return interpolate_grad_fast<3, false, true>;
+    case 14: return interpolate_grad_fast<3, true,  false>;  case 15: return interpolate_grad_fast<3, true,  true>;
+    case 16: return interpolate_grad_fast<4, false, false>;  case 17: return interpolate_grad_fast<4, false, true>;
+    case 18: return interpolate_grad_fast<4, true,  false>;  case 19: return interpolate_grad_fast<4, true,  true>;
     }
-    return n > 0 ? n : 1;
+    return 0;
+}
+
+// Launch of the templated backward (p filled; p.pos != 0 selects the fused rasterize backward).  Shared accumulators (g_attr, and
+// this image's g_pos when fused) are used when they fit; the grid is then exactly the resident wave (every CTA zeroes and flushes
+// its copies once), rounded DOWN so that no CTA is left over for a second wave; global accumulation: a few waves.
+static int launch_grad_fast(InterpParams& p, bool da, cudaStream_t stream, const char* fn)
+{
+    const bool raster = p.pos != 0;
+    const int A = p.A, N = p.N;
+    size_t stage_b = (size_t)(IP_THREADS / 32) * 32 * ((A == 3) ? (da ? 6 : 3) : 1) * sizeof(float);
+    size_t acc_b = (size_t)p.V * A * sizeof(float);
+    size_t pos_b = raster ? (size_t)p.Vp * 4 * sizeof(float) : 0;
+    p.use_smem_acc = (acc_b + stage_b <= 64 * 1024 && p.V <= ACC_SMEM_MAX_V) ? 1 : 0;
+    p.use_smem_pos = (raster && p.Vp <= IPC_SMEM_MAX_VP && pos_b + stage_b + (p.use_smem_acc ? acc_b : 0) <= 64 * 1024) ? 1 : 0;
+    size_t smem_f = stage_b + (p.use_smem_acc ? acc_b : 0) + (p.use_smem_pos ? pos_b : 0);
+    IpgKernel k = grad_fast_kernel(A, da, raster);
+    if (smem_f > 48 * 1024) B200DR_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), fn);
+    int groups = (int)(((size_t)p.H * p.W + 31) / 32);
+    const int unroll = da ? IPG_UNROLL_DA : IPG_UNROLL_PLAIN;
+    int gx = (groups + (IP_THREADS / 32) * unroll - 1) / ((IP_THREADS / 32) * unroll);
+    int capx = (b200dr_num_sms() * 12 + N - 1) / N;
+    if (p.use_smem_acc || p.use_smem_pos)
+    {
+        int resident = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, (const void*)k, IP_THREADS, smem_f);
+        capx = max(b200dr_num_sms() * max(resident, 1) / N, 1);
+    }
+    if (gx > capx) gx = capx;
+    if (gx < 1) gx = 1;
+    k<<<dim3(gx, N), IP_THREADS, smem_f, stream>>>(p);
+    return 0;
 }
 
 static int fill_params(InterpParams& p, const char* fn, const float* attr, const float* rast, const int32_t* tri, const float* rast_db,
@@ -657,32 +758,7 @@ extern "C" int b200dr_interpolate_grad(const float* attr, const float* rast, con
 
     if (fast_ok(p, da, attr) && B200DR_ALIGNED16(dy) && B200DR_ALIGNED16(g_attr) && (!da || (((uintptr_t)dda) & 31) == 0))
     {
-        size_t stage_b = (size_t)(IP_THREADS / 32) * 32 * ((A == 3) ? (da ? 6 : 3) : 1) * sizeof(float);
-        size_t acc_b = (size_t)V * A * sizeof(float);
-        p.use_smem_acc = (acc_b + stage_b <= 64 * 1024 && V <= ACC_SMEM_MAX_V) ? 1 : 0;
-        size_t smem_f = stage_b + (p.use_smem_acc ? acc_b : 0);
-        int groups = (int)(((size_t)H * W + 31) / 32);
-        const int unroll = da ? IPG_UNROLL_DA : IPG_UNROLL_PLAIN;
-        int gx = (groups + (IP_THREADS / 32) * unroll - 1) / ((IP_THREADS / 32) * unroll);
-        if (smem_f > 48 * 1024)
-        {
-            switch (A * 2 + (da ? 1 : 0)) {
-            case 2: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
-            case 3: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<1, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
-            case 4: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
-            case 5: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<2, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
-            case 6: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
-            case 7: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<3, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
-            case 8: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
-            case 9: B200DR_CUDA(cudaFuncSetAttribute(interpolate_grad_fast<4, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "interpolate()"); break;
-            }
-        }
-        // shared accumulators: exactly the resident wave (every CTA zeroes and flushes V*A sums once), rounded DOWN so that no
-        // CTA is left over for a second wave; global accumulation: a few waves
-        int capx = p.use_smem_acc ? max(b200dr_num_sms() * grad_fast_resident(A, da, smem_f) / N, 1) : (b200dr_num_sms() * 12 + N - 1) / N;
-        if (gx > capx) gx = capx;
-        if (gx < 1) gx = 1;
-        IP_DISPATCH(interpolate_grad_fast, A, da, dim3(gx, N), smem_f, stream, p);
+        if (launch_grad_fast(p, da, stream, "interpolate_grad()")) return 1;
         B200DR_CHECK_LAUNCH("interpolate_grad()");
         return 0;
     }
@@ -710,5 +786,31 @@ extern "C" int b200dr_interpolate_grad(const float* attr, const float* rast, con
         interpolate_grad_kernel<false><<<grid, IP_THREADS, smem, stream>>>(p);
     }
     B200DR_CHECK_LAUNCH("interpolate_grad()");
+    return 0;
+}
+
+// EXTENSION (include/b200dr.h): backward of interpolate(attr, rasterize(pos)) in one pass.
+extern "C" int b200dr_interpolate_chain_grad(const float* attr, const float* rast, const int32_t* tri, const float* dy,
+                                             const float* rast_db, const float* dda,
+                                             const float* pos, const int32_t* pos_tri, int Vp, int grad_db,
+                                             int N, int H, int W, int V, int T, int A, int attr_bc, int instance_mode, int diff_all,
+                                             float* g_attr, float* g_pos, void* stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const char* fn = "interpolate_chain_grad()";
+    InterpParams p = {};
+    const bool da = diff_all != 0;
+    if (fill_params(p, fn, attr, rast, tri, da ? rast_db : 0, N, H, W, V, T, A, attr_bc, instance_mode, da ? 1 : 0, 0, 0)) return 1;
+    if (!da) p.D = 0;
+    B200DR_CHECK(pos && pos_tri && g_pos && g_attr && dy && Vp > 0, "%s: missing input or output", fn);
+    B200DR_CHECK(!da || (rast_db && dda), "%s: rast_db and dda are required with differentials", fn);
+    B200DR_CHECK(fast_ok(p, da, attr), "%s: at most 4 attributes (all of them differentiated, or none), 8/16-byte aligned rows", fn);
+    B200DR_CHECK(B200DR_ALIGNED16(dy) && B200DR_ALIGNED16(g_attr) && B200DR_ALIGNED16(pos) && B200DR_ALIGNED16(g_pos) && (!da || (((uintptr_t)dda) & 31) == 0),
+                 "%s: tensor misaligned", fn);
+    p.dy = dy; p.dda = dda; p.g_attr = g_attr;
+    p.pos = pos; p.pos_tri = pos_tri; p.g_pos = g_pos; p.Vp = Vp; p.grad_db = grad_db;
+    p.xs = 2.f / (float)W; p.xo = 1.f / (float)W - 1.f; p.ys = 2.f / (float)H; p.yo = 1.f / (float)H - 1.f;
+    if (launch_grad_fast(p, da, stream, fn)) return 1;
+    B200DR_CHECK_LAUNCH(fn);
     return 0;
 }

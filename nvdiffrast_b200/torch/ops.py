@@ -81,12 +81,18 @@ def _require(cond, fn, msg):
 # executed unless another consumer (antialias's own pos gradient is separate) needs them; autograd sums the paths as usual.
 # Anything the proof does not cover (views, in-place edits, hooks or retain_grad on the intermediates, custom mip stacks,
 # mip_level_bias, cube maps, more than 4 channels, attribute counts other than 2) takes the op-by-op path.
+#
+# The same proof one level down: `interpolate()` handed the untouched outputs of an instanced-mode rasterize(pos, ...) registers
+# a backward node that goes from (dy, dda) to (g_attr, g_pos) in one kernel (b200dr_interpolate_chain_grad; up to 4 attributes,
+# differentials for all of them or none) -- chains without a texture (BASELINE's c2 / c4) and chains whose texture op cannot be
+# fused (cube maps, > 4 channels) skip the g_rast / g_rast_db round trip this way.
 
 _fusion_enabled = os.environ.get("B200DR_FUSION", "1") not in ("0", "false", "off")
 
 
 def set_fusion(enabled):
-    """Enable / disable the fused texture -> interpolate -> rasterize backward (default: enabled; env B200DR_FUSION=0)."""
+    """Enable / disable the fused backward nodes (texture -> interpolate -> rasterize, interpolate -> rasterize); default: enabled
+    (env B200DR_FUSION=0 disables)."""
     global _fusion_enabled
     _fusion_enabled = bool(enabled)
 
@@ -444,6 +450,74 @@ class _interpolate_func(torch.autograd.Function):
         return g_attr, g_rast, None
 
 
+def _aligned(t, nbytes):
+    """t, or a fresh copy when its address is not a multiple of nbytes (views with a storage offset)."""
+    return t if t is None or t.data_ptr() % nbytes == 0 else t.clone(memory_format=torch.contiguous_format)
+
+
+def _interpolate_chain_grad(attr, rast, tri, dy, rast_db, dda, pos, pos_tri, grad_db):
+    """Host side of b200dr_interpolate_chain_grad (include/b200dr.h): -> (g_attr, g_pos)."""
+    da = rast_db is not None
+    fn = "interpolate_chain_grad"
+    _lib.load()
+    dev = _check_inputs(fn, f32=[("attr", attr), ("rast", rast), ("rast_db", rast_db), ("pos", pos)], i32=[("tri", tri), ("pos_tri", pos_tri)])
+    _check_inputs(fn, f32=[("attr", attr), ("dy", dy), ("dda", dda if da else None)], contiguous=False)
+    N, H, W, V, A, inst, bc = _interp_dims(fn, attr, rast, tri, rast_db)
+    _require(pos.dim() == 3 and pos.shape[0] == N and pos.shape[2] == 4, fn, "pos must have shape [minibatch_size, num_vertices, 4]")
+    _require(pos_tri.shape == tri.shape, fn, "attribute and position index buffers must describe the same triangles")
+    _require(tuple(dy.shape) == (N, H, W, A), fn, "dy must have shape [minibatch_size, height, width, num_attributes]")
+    dy = _aligned(dy.contiguous(), 16)
+    if da:
+        _require(tuple(dda.shape) == (N, H, W, 2 * A), fn, "dda must have shape [minibatch_size, height, width, 2 * num_attributes]")
+        dda = _aligned(dda.contiguous(), 32)
+    with torch.cuda.device(dev):
+        g_attr = torch.zeros_like(attr)
+        g_pos = torch.zeros_like(pos)
+        _lib.call("b200dr_interpolate_chain_grad", _ptr(attr), _ptr(rast), _ptr(tri), _ptr(dy), _ptr(rast_db), _ptr(dda) if da else None,
+                  _ptr(pos), _ptr(pos_tri), pos.shape[1], int(grad_db), N, H, W, V, tri.shape[0], A, bc, inst, int(da),
+                  _ptr(g_attr), _ptr(g_pos), _stream(dev))
+    return g_attr, g_pos
+
+
+class _interpolate_chain_func(torch.autograd.Function):
+    """interpolate() whose backward also runs rasterize's (one kernel).  Differentiable inputs: attr and pos; rast / rast_db enter
+    as constants (they are proven to be the untouched outputs of rasterize(pos, pos_tri))."""
+
+    @staticmethod
+    def forward(ctx, attr, pos, rast, rast_db, tri, pos_tri, grad_db):
+        out, out_da = _interpolate_fwd(attr, rast, tri, rast_db, 1 if rast_db is not None else 0, [])
+        ctx.save_for_backward(attr, pos, rast, tri, pos_tri, rast_db if rast_db is not None else torch.tensor([]))
+        ctx.saved_misc = grad_db, rast_db is not None
+        return out, out_da
+
+    @staticmethod
+    def backward(ctx, dy, dda):
+        attr, pos, rast, tri, pos_tri, rast_db = ctx.saved_tensors
+        grad_db, da = ctx.saved_misc
+        g_attr, g_pos = _interpolate_chain_grad(attr, rast, tri, dy, rast_db if da else None, dda if da else None, pos, pos_tri, grad_db)
+        return g_attr, g_pos, None, None, None, None, None
+
+
+def _interp_fusion_plan(attr, rast, tri, rast_db, want_all, which):
+    """-> (pos, pos_tri, grad_db) when interpolate's backward can carry on through rasterize's in one kernel, else None."""
+    if not (_fusion_enabled and torch.is_grad_enabled()) or which:
+        return None
+    if not (attr.is_cuda and attr.dtype == torch.float32 and attr.is_contiguous() and attr.dim() in (2, 3) and 1 <= attr.shape[-1] <= 4
+            and attr.data_ptr() % 16 == 0):
+        return None
+    rprov = getattr(rast, "_b200dr_prov", None)
+    if rprov is None or rprov.kind != "rasterize" or not _pristine(rast, rprov, 0):
+        return None
+    pos, pos_tri = rprov.inputs
+    if pos.dim() != 3 or not pos.requires_grad or pos.data_ptr() % 16 != 0 or not pos.is_contiguous():
+        return None
+    if not (isinstance(tri, torch.Tensor) and tri.shape == pos_tri.shape):
+        return None
+    if want_all and (rast_db is None or not _pristine(rast_db, rprov, 1)):
+        return None
+    return pos, pos_tri, bool(rprov.meta["grad_db"])
+
+
 def _diff_attr_arg(diff_attrs):
     """`diff_attrs` of interpolate(): None | 'all' | 1-D sequence of attribute indices  ->  (all?, [indices])
     (same accepted forms as nvdiffrast/torch/ops.py:276-284)."""
@@ -486,11 +560,17 @@ def interpolate(attr, rast, tri, rast_db=None, diff_attrs=None):
         assert isinstance(t, torch.Tensor), "%s must be a tensor" % name
     if want_all or which:
         assert isinstance(rast_db, torch.Tensor), "diff_attrs needs rast_db"
+    else:
+        rast_db = None
+    plan = _interp_fusion_plan(attr, rast, tri, rast_db, want_all, which)
+    if plan is not None:
+        # rast / rast_db enter as constants (detached): this node owns the path (out, out_da) -> (attr, pos)
+        out = _interpolate_chain_func.apply(attr, plan[0], rast.detach(), rast_db.detach() if want_all else None, tri, plan[1], plan[2])
+    elif want_all or which:
         out = _interpolate_func_da.apply(attr, rast, tri, rast_db, int(want_all), which)
-        _Provenance("interpolate", (attr, rast, tri, rast_db), out, diff_all=want_all)
-        return out
-    out = _interpolate_func.apply(attr, rast, tri)
-    _Provenance("interpolate", (attr, rast, tri, None), out, diff_all=False)
+    else:
+        out = _interpolate_func.apply(attr, rast, tri)
+    _Provenance("interpolate", (attr, rast, tri, rast_db), out, diff_all=want_all)
     return out
 
 

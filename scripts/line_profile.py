@@ -1,12 +1,13 @@
 """Per-source-line executed-instruction profile: joins `nvdisasm -g -c` line info of one kernel with the per-SASS-instruction
 counters of an `ncu --page source --csv` export (same instruction order).
 
-    python scripts/line_profile.py <cubin> <mangled-kernel-substring> <ncu_source.csv> [top]
+    python scripts/line_profile.py <cubin> <mangled-kernel-substring> <ncu_source.csv> [top] [stall]
 """
 import collections, csv, re, subprocess, sys
 
 cubin, kern, ncsv = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+by_stall = len(sys.argv) > 5 and sys.argv[5] == "stall"      # order by stall samples instead of executed instructions
 txt = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.split("\n")
 # locate the function's text section
 start = next(i for i, l in enumerate(txt) if l.startswith("_Z") and kern in l and l.rstrip().endswith(":"))
@@ -40,5 +41,6 @@ def text(f, n):
         except Exception: src[f] = []
     return src[f][n - 1].strip()[:110] if 0 < n <= len(src[f]) else ""
 print("total warp-inst %d, samples %d" % (tex, tsm))
-for cur, v in ex.most_common(top):
+for cur, _ in (sm if by_stall else ex).most_common(top):
+    v = ex[cur]
     print("%5.1f%% ex %5.1f%% stall  %s:%d  %s" % (100 * v / tex, 100 * sm[cur] / max(tsm, 1), cur[0] if cur else "?", cur[1] if cur else 0, text(*cur) if cur else ""))

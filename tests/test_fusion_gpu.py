@@ -1,4 +1,5 @@
-"""Fused chain backward (texture -> interpolate -> rasterize in one kernel, nvdiffrast_b200/torch/ops.py `_fusion_plan`):
+"""Fused chain backwards (texture -> interpolate -> rasterize in one kernel, nvdiffrast_b200/torch/ops.py `_fusion_plan`;
+interpolate -> rasterize in one kernel, `_interp_fusion_plan`):
 same results as the op-by-op path, engaged only when the provenance of uv / uv_da / rast / rast_db is proven, and summed
 correctly with every other gradient path.  Tolerance: forward 1e-6 (same kernels; antialias' atomic blend order varies); accumulated gradients
 |d|_inf <= 2e-5 |g|_inf (only the summation order differs); per-pixel gradients abs 1e-6 |g|_inf + rel 1e-5."""
@@ -132,7 +133,8 @@ def test_fused_chain_with_other_consumers_of_the_intermediates(dr, ctx, c3):
     """uv and rast feed the loss directly as well: their own backward nodes run for those paths, the fused node for the
     texture path, autograd adds them up."""
     ops = _compare(dr, ctx, c3, 2, extra_uv_loss=True)
-    assert "interpolate_grad" in ops and "rasterize_grad" in ops
+    # texc's own path goes through the fused interpolate -> rasterize node, rast's direct consumer through rasterize's node
+    assert "interpolate_chain_grad" in ops and "rasterize_grad" in ops
 
 
 def test_fused_chain_stops_at_rast_in_range_mode(dr, ctx, c3):
@@ -161,3 +163,132 @@ def test_fullsize_fused_chain_c3(dr, ctx):
     for k in g_u:
         d = float((g_f[k].double() - g_u[k].double()).abs().max()); sc = float(g_u[k].abs().max())
         assert d <= 5e-5 * sc, "%s: |d|_inf %.3g vs |g|_inf %.3g" % (k, d, sc)
+
+
+# ----------------------------------------------------------------------------------------------
+# interpolate -> rasterize in one kernel (b200dr_interpolate_chain_grad)
+
+
+def _interp_chain(dr, ctx, pos_np, tri_np, attr_np, res, *, da=False, attr_mode="broadcast", grad_db=True, need=("pos", "attr"), tamper=None,
+                  peel_layers=0, use_db_loss=False):
+    tri = cu(tri_np)
+    pos = cu(pos_np).requires_grad_("pos" in need)
+    n = pos.shape[0]
+    if attr_mode == "per_image":
+        attr = cu(attr_np)[None].repeat(n, 1, 1).contiguous() * torch.linspace(1.0, 1.3, n, device="cuda")[:, None, None]
+    elif attr_mode == "broadcast":
+        attr = cu(attr_np)[None].contiguous()
+    else:                                                       # range-mode attributes [V, A] with instanced-mode positions
+        attr = cu(attr_np)
+    attr = attr.requires_grad_("attr" in need)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(23)
+    outs = []
+
+    def shade(rast, db):
+        if tamper == "view":
+            rast = rast[:, :, :, :]
+        elif tamper == "retain":
+            rast.retain_grad()
+        elif tamper == "foreign_db":
+            db = db * 1.0
+        o, oda = dr.interpolate(attr, rast, tri, rast_db=db if da else None, diff_attrs="all" if da else None)
+        outs.append(o); loss = (o * torch.randn(o.shape, device="cuda", generator=gen)).sum()
+        if da:
+            outs.append(oda); loss = loss + (oda * torch.randn(oda.shape, device="cuda", generator=gen)).sum()
+        if use_db_loss:
+            loss = loss + (db * torch.randn(db.shape, device="cuda", generator=gen)).sum() + (rast[..., :3] * 0.25).sum()
+        return loss
+
+    if peel_layers:
+        loss = 0.0
+        with dr.DepthPeeler(ctx, pos, tri, res, grad_db=grad_db) as peeler:
+            for _ in range(peel_layers):
+                rast, db = peeler.rasterize_next_layer()
+                loss = loss + shade(rast, db)
+    else:
+        rast, db = dr.rasterize(ctx, pos, tri, res, grad_db=grad_db)
+        loss = shade(rast, db)
+    _, ops = _ops_called(lambda: loss.backward())
+    grads = {"pos": pos.grad, "attr": attr.grad}
+    return [o.detach() for o in outs], {k: v for k, v in grads.items() if v is not None}, ops
+
+
+def _compare_interp(dr, ctx, *args, expect_fused=True, tol=2e-5, **kw):
+    dr.set_fusion(True)
+    outs_f, g_f, ops_f = _interp_chain(dr, ctx, *args, **kw)
+    dr.set_fusion(False)
+    try:
+        outs_u, g_u, ops_u = _interp_chain(dr, ctx, *args, **kw)
+    finally:
+        dr.set_fusion(True)
+    assert "interpolate_chain_grad" not in ops_u and "interpolate_grad" in ops_u
+    assert ("interpolate_chain_grad" in ops_f) == expect_fused, ops_f
+    if expect_fused and not kw.get("use_db_loss"):
+        assert "interpolate_grad" not in ops_f and "rasterize_grad" not in ops_f, ops_f
+    for a, b in zip(outs_f, outs_u):
+        assert torch.equal(a, b)                                # the forward kernel is the same
+    assert set(g_f) == set(g_u) and len(g_u) > 0
+    for k in g_u:
+        d = float((g_f[k].double() - g_u[k].double()).abs().max()); sc = float(g_u[k].abs().max())
+        assert sc > 0 and d <= tol * sc, "%s: |d|_inf %.3g vs |g|_inf %.3g" % (k, d, sc)
+    return ops_f
+
+
+@pytest.fixture(scope="module")
+def c2s():
+    c = wl.config_c2(n=3, res=320)
+    return c["pos"], c["tri"], c["attr"], c["res"]
+
+
+@pytest.fixture(scope="module")
+def sph():
+    """c3's sphere (2 930 vertices: position gradients accumulate in global memory), 3 attributes from the uv table."""
+    c = wl.config_c3(n=2, res=384, tex_res=64)
+    rng = np.random.RandomState(5)
+    return c["pos"], c["tri"], rng.randn(c["pos"].shape[1], 4).astype(np.float32), c["res"]
+
+
+@pytest.mark.parametrize("A", [1, 2, 3, 4])
+@pytest.mark.parametrize("da", [False, True])
+def test_interp_chain_matches_op_by_op_small_mesh(dr, ctx, c2s, A, da):
+    """c2's cube (8 vertices: shared-memory accumulators for both gradients)."""
+    pos, tri, attr, res = c2s
+    rng = np.random.RandomState(A)
+    _compare_interp(dr, ctx, pos, tri, rng.randn(attr.shape[0], A).astype(np.float32), res, da=da)
+
+
+@pytest.mark.parametrize("A", [1, 2, 3, 4])
+@pytest.mark.parametrize("da", [False, True])
+def test_interp_chain_matches_op_by_op_sphere(dr, ctx, sph, A, da):
+    pos, tri, attr, res = sph
+    _compare_interp(dr, ctx, pos, tri, np.ascontiguousarray(attr[:, :A]), res, da=da)
+
+
+@pytest.mark.parametrize("kw", [dict(attr_mode="per_image"), dict(attr_mode="range"), dict(grad_db=False, da=True), dict(need=("pos",)),
+                                dict(attr_mode="per_image", da=True), dict(peel_layers=3, da=True), dict(use_db_loss=True, da=True)])
+def test_interp_chain_modes(dr, ctx, sph, kw):
+    pos, tri, attr, res = sph
+    _compare_interp(dr, ctx, pos, tri, np.ascontiguousarray(attr[:, :3]), res, **kw)
+
+
+@pytest.mark.parametrize("kw", [dict(tamper="view"), dict(tamper="retain"), dict(tamper="foreign_db", da=True), dict(need=("attr",))])
+def test_interp_chain_unproven_provenance_takes_the_op_by_op_path(dr, ctx, sph, kw):
+    pos, tri, attr, res = sph
+    _compare_interp(dr, ctx, pos, tri, np.ascontiguousarray(attr[:, :3]), res, expect_fused=False, **kw)
+
+
+def test_interp_chain_partial_diff_list_takes_the_op_by_op_path(dr, ctx, sph):
+    pos_np, tri_np, attr_np, res = sph
+    pos = cu(pos_np).requires_grad_(True); attr = cu(attr_np[:, :3].copy())[None].requires_grad_(True)
+    rast, db = dr.rasterize(ctx, pos, cu(tri_np), res)
+    o, oda = dr.interpolate(attr, rast, cu(tri_np), rast_db=db, diff_attrs=[0, 2])
+    _, ops = _ops_called(lambda: (o.sum() + oda.sum()).backward())
+    assert "interpolate_chain_grad" not in ops and "interpolate_grad" in ops and "rasterize_grad" in ops
+
+
+def test_fullsize_interp_chain_c2_and_c4(dr, ctx):
+    """BASELINE's c2 (1024^2 x 8 here) and c4 (1M triangles, 2048^2 x 1): fused == op-by-op."""
+    c = wl.config_c2(n=8, res=1024)
+    _compare_interp(dr, ctx, c["pos"], c["tri"], c["attr"], c["res"], tol=5e-5)
+    c = wl.config_c4(n=1, res=2048)
+    _compare_interp(dr, ctx, c["pos"], c["tri"], c["attr"], c["res"], tol=5e-5)
