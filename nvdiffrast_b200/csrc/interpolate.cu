@@ -385,14 +385,18 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_fwd_fast(const InterpP
 
 // RASTER: the rasterizer's backward is applied in the same pass (b200dr_interpolate_chain_grad): per pixel, (g_rast.xy, g_rast_db)
 // go through pm::raster_grad instead of memory, and the vertex-position gradients are summed over the same triangle runs.
+// r02 call 14 (c2 / c4 fused kernel): 4 CTAs/SM at 64 registers 0.638 / 0.715 ms; 3 CTAs at 80 registers 0.810 / 0.767; 2 CTAs the same
 #ifndef IPC_MINB
-#define IPC_MINB 3
+#define IPC_MINB 4
+#endif
+#ifndef IPC_UNROLL
+#define IPC_UNROLL 4
 #endif
 #define IPC_SMEM_MAX_VP 1024    // position gradients of one image in shared memory up to this many vertices (as raster_grad_kernel)
 template <int A, bool DA, bool RASTER>
 __global__ void __launch_bounds__(IP_THREADS, RASTER ? IPC_MINB : (DA ? IPG_MINB_DA : IPG_MINB_PLAIN)) interpolate_grad_fast(const InterpParams p)
 {
-    constexpr int IPG_UNROLL = DA ? IPG_UNROLL_DA : IPG_UNROLL_PLAIN;
+    constexpr int IPG_UNROLL = RASTER ? IPC_UNROLL : (DA ? IPG_UNROLL_DA : IPG_UNROLL_PLAIN);
     extern __shared__ __align__(16) float s_dyn[];
     constexpr int SK = (A == 3) ? (DA ? 6 : 3) : 1;
     float* s_stage = s_dyn;                                             // [8 warps][32 * SK]
@@ -658,7 +662,7 @@ static int launch_grad_fast(InterpParams& p, bool da, cudaStream_t stream, const
     IpgKernel k = grad_fast_kernel(A, da, raster);
     if (smem_f > 48 * 1024) B200DR_CUDA(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), fn);
     int groups = (int)(((size_t)p.H * p.W + 31) / 32);
-    const int unroll = da ? IPG_UNROLL_DA : IPG_UNROLL_PLAIN;
+    const int unroll = raster ? IPC_UNROLL : (da ? IPG_UNROLL_DA : IPG_UNROLL_PLAIN);
     int gx = (groups + (IP_THREADS / 32) * unroll - 1) / ((IP_THREADS / 32) * unroll);
     int capx = (b200dr_num_sms() * 12 + N - 1) / N;
     if (p.use_smem_acc || p.use_smem_pos)

@@ -37,6 +37,7 @@ struct RastParams
     uint32_t*       depth_out;
     // BINS scratch
     int*            extra;          // [N] extra (clipped) sub-triangle counters
+    uint32_t*       binmask;        // [N, 32] row y, bit x: some triangle's bounding box touches bin (x, y) of the current viewport
     uint2*          bbox;           // [N, cap]
     uint2*          cbox;           // [N, nchunk]: union of the bounding boxes of 32 consecutive triangle slots ("chunk")
     int             nchunk;         // chunk boxes per image (even, so that every image's array is a 16-byte aligned TMA source)
@@ -289,6 +290,10 @@ static __device__ __forceinline__ Edge make_edge(int ax, int ay, int bx, int by,
 #define BIN_THREADS 256
 #define B200DR_BINS_MAX_TRIS 49152
 #define BIN_MAXCHUNK 1024       // chunk boxes staged per TMA slab (32768 triangles); larger images re-stage
+#define BIN_ROWS   32           // a viewport is at most 2048 = 32 * BIN_SIZE pixels wide and high: one mask word per bin row
+#ifndef BIN_MASK
+#define BIN_MASK 1              // bins no bounding box touches are cleared without scanning anything
+#endif
 
 struct __align__(16) BinTri     // 64 bytes, broadcast-read by every thread of the CTA
 {
@@ -297,6 +302,13 @@ struct __align__(16) BinTri     // 64 bytes, broadcast-read by every thread of t
     int e2sy; uint32_t zc, zx, zy;
     uint32_t id, box, pad0, pad1;   // box = x0 | x1<<8 | y0<<16 | y1<<24, bin-relative pixels
 };
+
+static __device__ __forceinline__ void mark_bins(uint32_t* rows, int x0, int x1, int y0, int y1)
+{
+    if (x0 > x1 || y0 > y1) return;
+    const uint32_t bits = (0xFFFFFFFFu >> (31 - (x1 >> BIN_LOG2))) & (0xFFFFFFFFu << (x0 >> BIN_LOG2));
+    for (int by = y0 >> BIN_LOG2; by <= (y1 >> BIN_LOG2); by++) atomicOr(rows + by, bits);
+}
 
 struct SetupEmitRecords
 {
@@ -308,6 +320,7 @@ struct SetupEmitRecords
         size_t base = (size_t)n * p.cap + slot;
         const uint2 box = make_uint2((uint32_t)s.bx0 | ((uint32_t)s.bx1 << 16), (uint32_t)s.by0 | ((uint32_t)s.by1 << 16));
         if (emitted == 0) first = box;
+        else if (BIN_MASK) mark_bins(p.binmask + n * BIN_ROWS, s.bx0, s.bx1, s.by0, s.by1);    // extras are not covered by the chunk boxes
         emitted++;
         p.bbox[base] = box;
         p.rec[base * 2 + 0] = make_uint4(((uint32_t)s.x0 & 0xFFFFu) | ((uint32_t)s.y0 << 16), ((uint32_t)s.x1 & 0xFFFFu) | ((uint32_t)s.y1 << 16),
@@ -385,7 +398,10 @@ __global__ void __launch_bounds__(128) raster_setup_kernel(const RastParams p)
         y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, d)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, d));
     }
     if ((threadIdx.x & 31) == 0 && (t >> 5) < p.nchunk)
+    {
         p.cbox[(size_t)n * p.nchunk + (t >> 5)] = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
+        if (BIN_MASK && x0 <= x1) mark_bins(p.binmask + n * BIN_ROWS, x0, x1, y0, y1);
+    }
 }
 
 static __device__ __forceinline__ int s16lo(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
@@ -416,6 +432,24 @@ __global__ void __launch_bounds__(BIN_THREADS, BIN_MINB) raster_bins_kernel(cons
     const int wx = (warp & 1) << 5, wy = (warp >> 1) << 4;             // this warp's 32x16 region, bin-relative
     const int tx = wx + ((lane & 7) << 2);
     const int ty = wy + ((lane >> 3) << 2);
+
+    if (BIN_MASK && !((__ldg(p.binmask + n * BIN_ROWS + blockIdx.y) >> blockIdx.x) & 1u))
+    {
+        // no bounding box touches this bin (CTA-uniform): cleared pixels, cleared depth, nothing scanned
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        #pragma unroll 4
+        for (int k = 0; k < (BIN_SIZE * BIN_SIZE) / BIN_THREADS; k++)
+        {
+            const int q = tid + k * BIN_THREADS;
+            const int lx = q & (BIN_SIZE - 1), ly = q >> BIN_LOG2;
+            if (binX0 + lx >= p.vpW || binY0 + ly >= p.vpH) continue;
+            const size_t pi = ((size_t)n * p.H + p.offY + binY0 + ly) * p.W + p.offX + binX0 + lx;
+            st_stream_f4((float4*)p.rast + pi, zero);
+            st_stream_f4((float4*)p.rast_db + pi, zero);
+            if (DEPTH_OUT) p.depth_out[pi] = DR_DEPTH_MAX;
+        }
+        return;
+    }
 
     if (tid == 0) mbar_init(&s_mbar, 1);
 
@@ -984,7 +1018,7 @@ extern "C" size_t b200dr_rasterize_scratch_bytes(int N, int max_tris, int H, int
     {
         size_t cap = ((size_t)7 * max_tris + 1) & ~(size_t)1;
         size_t nchunk = ((((size_t)max_tris + 31) >> 5) + 1) & ~(size_t)1;   // even: every image's chunk-box array stays a 16-byte aligned TMA source
-        return align_up((size_t)N * sizeof(int), 256) + align_up((size_t)N * nchunk * sizeof(uint2), 256) +
+        return align_up((size_t)N * (1 + BIN_ROWS) * sizeof(int), 256) + align_up((size_t)N * nchunk * sizeof(uint2), 256) +
                align_up((size_t)N * cap * sizeof(uint2), 256) + (size_t)N * cap * 2 * sizeof(uint4);
     }
     return (size_t)N * H * W * sizeof(unsigned long long);
@@ -1025,7 +1059,8 @@ extern "C" int b200dr_rasterize_fwd(const float* pos, const int32_t* tri, const 
     {
         char* s = (char*)scratch;
         p.nchunk = (((max_tris + 31) >> 5) + 1) & ~1;
-        p.extra = (int*)s;                    s += align_up((size_t)N * sizeof(int), 256);
+        p.extra = (int*)s; p.binmask = (uint32_t*)s + N;       // cleared together, once per viewport
+        s += align_up((size_t)N * (1 + BIN_ROWS) * sizeof(int), 256);
         p.cbox = (uint2*)s;                   s += align_up((size_t)N * p.nchunk * sizeof(uint2), 256);
         p.bbox = (uint2*)s;                   s += align_up((size_t)N * p.cap * sizeof(uint2), 256);
         p.rec = (uint4*)s;
@@ -1055,7 +1090,7 @@ extern "C" int b200dr_rasterize_fwd(const float* pos, const int32_t* tri, const 
         p.vyo = (float)(H - p.vpH - 2 * p.offY) / (float)p.vpH;
         if (path == B200DR_RAST_BINS)
         {
-            B200DR_CUDA(cudaMemsetAsync(p.extra, 0, (size_t)N * sizeof(int), stream), "rasterize()");
+            B200DR_CUDA(cudaMemsetAsync(p.extra, 0, (size_t)N * (1 + BIN_ROWS) * sizeof(int), stream), "rasterize()");
             raster_setup_kernel<<<dim3((max_tris + 127) / 128, N), 128, 0, stream>>>(p);
             B200DR_CHECK_LAUNCH("rasterize_fwd(setup)");
             dim3 grid((p.vpW + BIN_SIZE - 1) / BIN_SIZE, (p.vpH + BIN_SIZE - 1) / BIN_SIZE, N);
