@@ -386,11 +386,12 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_fwd_fast(const InterpP
 // RASTER: the rasterizer's backward is applied in the same pass (b200dr_interpolate_chain_grad): per pixel, (g_rast.xy, g_rast_db)
 // go through pm::raster_grad instead of memory, and the vertex-position gradients are summed over the same triangle runs.
 // r02 call 14 (c2 / c4 fused kernel): 4 CTAs/SM at 64 registers 0.638 / 0.715 ms; 3 CTAs at 80 registers 0.810 / 0.767; 2 CTAs the same
+// call 15: 2 groups in flight instead of 4 (half the code: ncu showed instruction-fetch stalls) 0.593 / 0.632; 5 CTAs/SM 0.607 / 0.749
 #ifndef IPC_MINB
 #define IPC_MINB 4
 #endif
 #ifndef IPC_UNROLL
-#define IPC_UNROLL 4
+#define IPC_UNROLL 2
 #endif
 #define IPC_SMEM_MAX_VP 1024    // position gradients of one image in shared memory up to this many vertices (as raster_grad_kernel)
 template <int A, bool DA, bool RASTER>

@@ -765,8 +765,11 @@ static __device__ __forceinline__ void scatter_subtri_warp(const RastParams& p, 
     }
 }
 
+#ifndef SCATTER_MINB
+#define SCATTER_MINB 1
+#endif
 template <bool PEEL_IN>
-__global__ void __launch_bounds__(128) raster_scatter_kernel(const RastParams p)
+__global__ void __launch_bounds__(128, SCATTER_MINB) raster_scatter_kernel(const RastParams p)
 {
     int t = blockIdx.x * 128 + threadIdx.x;     // whole warps stay alive: no early return before the warp collectives
     int n = blockIdx.y;
@@ -818,24 +821,61 @@ __global__ void __launch_bounds__(128) raster_scatter_kernel(const RastParams p)
     }
 }
 
+// Resolve pass of the SCATTER path: key -> (id, depth), pixel shader, stores.  The chain key -> triangle indices -> vertex positions
+// is three dependent gathers per pixel (ncu, 1 M triangles: long-scoreboard stalls 14 per issue): every thread walks RESOLVE_ILP
+// pixels at once, each stage issued for all of them before the next starts.  grid = (blocks, images): 32-bit pixel arithmetic.
+#ifndef RESOLVE_ILP
+#define RESOLVE_ILP 2
+#endif
 template <bool DEPTH_OUT>
 __global__ void __launch_bounds__(256) raster_resolve_kernel(const RastParams p)
 {
-    size_t hw = (size_t)p.H * p.W;
-    size_t total = hw * p.N;
-    for (size_t pi = (size_t)blockIdx.x * 256 + threadIdx.x; pi < total; pi += (size_t)gridDim.x * 256)
+    const unsigned hw = (unsigned)p.H * (unsigned)p.W;
+    const int n = blockIdx.y;
+    const size_t img = (size_t)n * hw;
+    const float4* vb = (const float4*)p.pos + (p.instance_mode ? (size_t)n * p.V : 0);
+    for (unsigned r0 = blockIdx.x * (256u * RESOLVE_ILP) + threadIdx.x; r0 < hw; r0 += gridDim.x * (256u * RESOLVE_ILP))
     {
-        unsigned long long key = p.keys[pi];
-        uint32_t low = (uint32_t)key;
-        int id = (int)(0xFFFFFFFFu - low) - 1;
-        int n = (int)(pi / hw);
-        size_t r = pi - (size_t)n * hw;
-        int Y = (int)(r / p.W), X = (int)(r - (size_t)Y * p.W);
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f), db = o;
-        if (id >= 0) shade_pixel(p, n, id, X, Y, o, db);
-        st_stream_f4((float4*)p.rast + pi, o);
-        st_stream_f4((float4*)p.rast_db + pi, db);
-        if (DEPTH_OUT) p.depth_out[pi] = (id >= 0) ? (uint32_t)(key >> 32) : DR_DEPTH_MAX;
+        unsigned long long key[RESOLVE_ILP];
+        int id[RESOLVE_ILP], vi[RESOLVE_ILP][3];
+        float4 v[RESOLVE_ILP][3];
+        #pragma unroll
+        for (int u = 0; u < RESOLVE_ILP; u++)
+        {
+            const unsigned r = r0 + u * 256u;
+            key[u] = (r < hw) ? p.keys[img + r] : 0xFFFFFFFFFFFFFFFFull;
+        }
+        #pragma unroll
+        for (int u = 0; u < RESOLVE_ILP; u++)
+        {
+            id[u] = (int)(0xFFFFFFFFu - (uint32_t)key[u]) - 1;
+            vi[u][0] = vi[u][1] = vi[u][2] = 0;
+            if (id[u] >= 0)
+            {
+                const int32_t* t = p.tri + (size_t)id[u] * 3;
+                vi[u][0] = __ldg(t); vi[u][1] = __ldg(t + 1); vi[u][2] = __ldg(t + 2);
+            }
+        }
+        #pragma unroll
+        for (int u = 0; u < RESOLVE_ILP; u++)
+            if (id[u] >= 0) { v[u][0] = __ldg(vb + vi[u][0]); v[u][1] = __ldg(vb + vi[u][1]); v[u][2] = __ldg(vb + vi[u][2]); }
+        #pragma unroll
+        for (int u = 0; u < RESOLVE_ILP; u++)
+        {
+            const unsigned r = r0 + u * 256u;
+            if (r >= hw) continue;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f), db = o;
+            if (id[u] >= 0)
+            {
+                const unsigned Y = r / (unsigned)p.W, X = r - Y * (unsigned)p.W;
+                pm::PixelTri t;
+                pm::pixel_tri(t, v[u][0], v[u][1], v[u][2], p.xs * (float)X + p.xo, p.ys * (float)Y + p.yo);
+                pm::shade(t, p.xs, p.ys, triidx_to_float(id[u] + 1), o, db);
+            }
+            st_stream_f4((float4*)p.rast + img + r, o);
+            st_stream_f4((float4*)p.rast_db + img + r, db);
+            if (DEPTH_OUT) p.depth_out[img + r] = (id[u] >= 0) ? (uint32_t)(key[u] >> 32) : DR_DEPTH_MAX;
+        }
     }
 }
 
@@ -1109,12 +1149,13 @@ extern "C" int b200dr_rasterize_fwd(const float* pos, const int32_t* tri, const 
     }
     if (path == B200DR_RAST_SCATTER)
     {
-        size_t total = (size_t)N * H * W;
-        int blocks = (int)((total + 255) / 256);
-        int maxb = b200dr_num_sms() * 16;
+        size_t per_image = (size_t)H * W;
+        int blocks = (int)((per_image + 256 * RESOLVE_ILP - 1) / (256 * RESOLVE_ILP));
+        int maxb = (b200dr_num_sms() * 16 + N - 1) / N;
         if (blocks > maxb) blocks = maxb;
-        if (depth_out) raster_resolve_kernel<true><<<blocks, 256, 0, stream>>>(p);
-        else           raster_resolve_kernel<false><<<blocks, 256, 0, stream>>>(p);
+        if (blocks < 1) blocks = 1;
+        if (depth_out) raster_resolve_kernel<true><<<dim3(blocks, N), 256, 0, stream>>>(p);
+        else           raster_resolve_kernel<false><<<dim3(blocks, N), 256, 0, stream>>>(p);
         B200DR_CHECK_LAUNCH("rasterize_fwd(resolve)");
     }
     return 0;
