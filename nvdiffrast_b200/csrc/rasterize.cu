@@ -766,7 +766,7 @@ static __device__ __forceinline__ void scatter_subtri_warp(const RastParams& p, 
 }
 
 #ifndef SCATTER_MINB
-#define SCATTER_MINB 1
+#define SCATTER_MINB 8      // 64 registers (28 bytes spilled), 8 CTAs/SM: c4 rasterize fwd 0.696 -> 0.673 ms; 10 CTAs (48 registers) 0.692
 #endif
 template <bool PEEL_IN>
 __global__ void __launch_bounds__(128, SCATTER_MINB) raster_scatter_kernel(const RastParams p)
@@ -822,10 +822,12 @@ __global__ void __launch_bounds__(128, SCATTER_MINB) raster_scatter_kernel(const
 }
 
 // Resolve pass of the SCATTER path: key -> (id, depth), pixel shader, stores.  The chain key -> triangle indices -> vertex positions
-// is three dependent gathers per pixel (ncu, 1 M triangles: long-scoreboard stalls 14 per issue): every thread walks RESOLVE_ILP
-// pixels at once, each stage issued for all of them before the next starts.  grid = (blocks, images): 32-bit pixel arithmetic.
+// is three dependent gathers per pixel (ncu, 1 M triangles: long-scoreboard stalls 14 per issue).  A thread can walk RESOLVE_ILP
+// pixels at once, each stage issued for all of them before the next starts -- measured on c4 (r02 call 16, rasterize fwd in ms):
+// 1 pixel 0.677, 2 pixels 0.696, 4 pixels 0.747: occupancy (32 registers, 80 % of the warp slots) hides the latency better than the
+// wider threads do, so the default stays 1.  grid = (blocks, images): 32-bit pixel arithmetic.
 #ifndef RESOLVE_ILP
-#define RESOLVE_ILP 2
+#define RESOLVE_ILP 1
 #endif
 template <bool DEPTH_OUT>
 __global__ void __launch_bounds__(256) raster_resolve_kernel(const RastParams p)
