@@ -388,24 +388,10 @@ static __device__ __forceinline__ void red_add3(float* p, float a, float b, floa
     else                           { red_add(p, a); red_add2(p + 1, make_float2(b, c)); }
 }
 
-// ---- L2 prefetch of a warp's NEXT pixel group (streaming kernels walk their tensors with a fixed grid stride, so the
-// addresses are known one iteration ahead).  Measured on c3 (profiles/r02_experiments.md): the bulk form (UBLKPF.L2, one
-// elected lane, goes through the TMA unit) SLOWS the texture kernels by 3-26 % at two to three 256-512 byte requests per
-// group and gains 1-2 % elsewhere; it is therefore off by default.  DR_PREFETCH = 1: bulk form; 2: one
-// prefetch.global.L2 per lane (LSU path, 16 bytes apart).  All lanes call; addr 16-byte aligned, bytes <= 512, multiple of 16.
-#ifndef DR_PREFETCH
-#define DR_PREFETCH 0
-#endif
-static __device__ __forceinline__ void warp_prefetch_l2(const void* addr, uint32_t bytes, int lane)
-{
-#if DR_PREFETCH == 1
-    if (lane == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(addr), "r"(bytes) : "memory");
-#elif DR_PREFETCH == 2
-    if ((uint32_t)lane * 16u < bytes) asm volatile("prefetch.global.L2 [%0];" :: "l"((const char*)addr + lane * 16) : "memory");
-#else
-    (void)addr; (void)bytes; (void)lane;
-#endif
-}
+// ---- L2 prefetch of a warp's NEXT pixel group: measured and removed from every short-iteration kernel (profiles/r02_experiments.md
+// section 2: the bulk form cp.async.bulk.prefetch.L2 goes through the TMA unit and slows the texture kernels by 3-26 %, the per-lane
+// prefetch.global.L2 costs the texture forward 18 % and gains <= 2 % elsewhere).  Only the fused chain backward, whose iterations
+// run for hundreds of instructions, keeps a per-lane prefetch (texture.cu, texture_chain_grad_fast).
 
 // ---- TMA bulk copy (1-D, global -> shared) with an mbarrier transaction count: cp.async.bulk / UBLKCP on sm_100a.
 // dst, src 16-byte aligned, bytes a multiple of 16.  One thread issues; every consumer waits on the barrier's phase.

@@ -325,14 +325,6 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_fwd_fast(const InterpP
             r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (inb[u]) r[u] = ld_stream_f4((const float4*)p.rast + img + px);
         }
-#if DR_PREFETCH
-        #pragma unroll
-        for (int u = 0; u < IPF_UNROLL; u++)
-        {
-            const int gn = g0 + (IPF_UNROLL + u) * wstride;
-            if (gn * 32 + 32 <= hw) warp_prefetch_l2((const float4*)p.rast + img + (size_t)gn * 32, 512, lane);
-        }
-#endif
         #pragma unroll
         for (int u = 0; u < IPF_UNROLL; u++)
         {
@@ -435,15 +427,6 @@ __global__ void __launch_bounds__(IP_THREADS, RASTER ? IPC_MINB : (DA ? IPG_MINB
             r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (inb[u]) r[u] = ld_stream_f4((const float4*)p.rast + img + px);
         }
-#if DR_PREFETCH
-        #pragma unroll
-        for (int u = 0; u < IPG_UNROLL; u++)
-        {
-            const int gn = g0 + (IPG_UNROLL + u) * wstride;
-            // only rast: dy / dda / rast_db are fetched under geometry only, prefetching them would add the bytes back
-            if (gn * 32 + 32 <= hw) warp_prefetch_l2((const float4*)p.rast + img + (size_t)gn * 32, 512, lane);
-        }
-#endif
         #pragma unroll
         for (int u = 0; u < IPG_UNROLL; u++)
         {

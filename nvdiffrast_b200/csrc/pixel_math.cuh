@@ -94,14 +94,9 @@ PM_HD void shade(const PixelTri& t, float xs, float ys, float id_as_float, float
 
     u = sat01(u);
     v = sat01(v);
-#ifdef PM_SHRINK_BRANCH
-    // same bits: for u + v <= 1 the quotient is exactly 1 and the products leave u, v unchanged
-    if (u + v > 1.f) { const float shrink = 1.f / (u + v); u *= shrink; v *= shrink; }
-#else
     const float shrink = 1.f / fmaxf(u + v, 1.f);       // pull (u, v) back onto the edge u + v = 1
     u *= shrink;
     v *= shrink;
-#endif
     depth = fmaxf(fminf(depth, 1.f), -1.f);
     rast = make_float4(u, v, depth, id_as_float);
 

@@ -955,14 +955,6 @@ __global__ void __launch_bounds__(256, RG_MINB) raster_grad_kernel(const RastGra
             ro[u] = make_float4(0.f, 0.f, 0.f, 0.f); ddb[u] = ro[u]; dy[u] = make_float2(0.f, 0.f);
             if (inb[u]) ro[u] = ld_stream_f4((const float4*)p.rast + img + r);
         }
-#if DR_PREFETCH
-        #pragma unroll
-        for (int u = 0; u < RG_UNROLL; u++)
-        {
-            const int gn = g0 + (RG_UNROLL + u) * wstride;
-            if (gn * 32 + 32 <= hw) warp_prefetch_l2((const float4*)p.rast + img + (size_t)gn * 32, 512, lane);
-        }
-#endif
         // incoming gradients are fetched only under geometry (empty pixels cost 16 instead of 40-48 bytes); the extra
         // dependency runs in parallel with the triangle -> vertex gathers
         #pragma unroll

@@ -627,18 +627,6 @@ __global__ void __launch_bounds__(TEX_THREADS, TEXF_MINB) texture_fwd_fast(const
                 if (mip && m.has_bias) bias[u] = ld_stream_f(p.bias + pidx);
             }
         }
-#if DR_PREFETCH
-        #pragma unroll
-        for (int u = 0; u < TEXF_UNROLL; u++)
-        {
-            const size_t gn = g0 + (TEXF_UNROLL + u) * wstride;
-            if (gn * 32 + 32 <= total)
-            {
-                warp_prefetch_l2(p.uv + gn * 64, 256, lane);
-                if (mip && m.has_da) warp_prefetch_l2(p.uv_da + gn * 128, 512, lane);
-            }
-        }
-#endif
         #pragma unroll
         for (int u = 0; u < TEXF_UNROLL; u++)
         {
@@ -1017,22 +1005,6 @@ __global__ void __launch_bounds__(TEXG_THREADS, TEXG_MINB) texture_grad_fast(con
         TexGradIn<C> in[TEXG_UNROLL];
         #pragma unroll
         for (int u = 0; u < TEXG_UNROLL; u++) texgrad_issue<C>(p, m, g0 + u * wstride, groups, total, lane, in[u]);
-#if DR_PREFETCH
-        if (!p.tile2d)
-        {
-            #pragma unroll
-            for (int u = 0; u < TEXG_UNROLL; u++)
-            {
-                const size_t gn = g0 + (TEXG_UNROLL + u) * wstride;
-                if (gn * 32 + 32 <= total)
-                {
-                    warp_prefetch_l2(p.dy + gn * 32 * C, 32 * C * 4, lane);
-                    warp_prefetch_l2(p.uv + gn * 64, 256, lane);
-                    if (m.has_da) warp_prefetch_l2(p.uv_da + gn * 128, 512, lane);
-                }
-            }
-        }
-#endif
         #pragma unroll
         for (int u = 0; u < TEXG_UNROLL; u++)
             if (in[u].g < groups) texgrad_group<C, B, true>(p, m, in[u], pd, cached, &s_slot[warp], lane, s_stage[warp], hw, trilinear);   // warp-uniform
