@@ -5,6 +5,8 @@
 The shared library is written next to this file (nvdiffrast_b200/libb200dr.so): git-ignored, but it travels to the
 GPU box with the gpurun snapshot.  No JIT cache, no torch extension machinery: plain nvcc -shared.
 """
+import contextlib
+import fcntl
 import os
 import subprocess
 import sys
@@ -41,12 +43,32 @@ def build_variant(name, defs):
     return build(force=True, defs=list(defs), out=out, bdir=os.path.join(_DIR, "csrc", "_build", "var_" + name))
 
 
+@contextlib.contextmanager
+def _build_lock(path):
+    """Exclusive inter-process lock: the ranks of one node import this package at the same moment, and each of them would start
+    the same nvcc jobs into the same object files (round 2: a 2-rank run loaded a library that the other rank was still linking)."""
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        fcntl.flock(f, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(f, fcntl.LOCK_UN)
+
+
 def build(force=False, verbose=False, defs=(), out=None, bdir=None):
     if not force and not needs_build():
         return SO_PATH
     out = out or SO_PATH
     bdir = bdir or os.path.join(_DIR, "csrc", "_build")
     os.makedirs(bdir, exist_ok=True)
+    with _build_lock(os.path.join(bdir, ".lock")):
+        if not force and out == SO_PATH and not needs_build():      # another process built it while this one waited for the lock
+            return SO_PATH
+        return _build_locked(verbose, defs, out, bdir)
+
+
+def _build_locked(verbose, defs, out, bdir):
     objs = []
     procs = []
     for src in SOURCES:
@@ -67,7 +89,10 @@ def build(force=False, verbose=False, defs=(), out=None, bdir=None):
         sys.stderr.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed, see %s" % os.path.join(bdir, "build.log"))
-    subprocess.check_call([_nvcc(), "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
+    # link to a temporary name and rename: a process that loads the library never sees a partially written file
+    tmp = "%s.tmp.%d" % (out, os.getpid())
+    subprocess.check_call([_nvcc(), "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
+    os.replace(tmp, out)
     return out
 
 

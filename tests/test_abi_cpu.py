@@ -165,3 +165,23 @@ def test_header_is_plain_c_and_the_c_example_links():
         subprocess.check_call([gcc, "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
                                os.path.join(ROOT, "examples", "c_abi_triangle.c"), "-o", os.path.join(tmp, "t"),
                                "-L", os.path.dirname(_lib.so_path()), "-lb200dr", "-L", os.path.join(cuda, "lib64"), "-lcudart"])
+
+
+def test_concurrent_builds_are_serialised():
+    """Two processes that find the sources newer than the library (the ranks of one node at start-up) must not write the same object
+    files at once: the build takes an inter-process lock and installs the library by rename."""
+    import subprocess, sys, time
+    from nvdiffrast_b200 import build as b
+    if b._nvcc() == "nvcc" and not any(os.access(os.path.join(d, "nvcc"), os.X_OK) for d in os.environ.get("PATH", "").split(os.pathsep)):
+        pytest.skip("nvcc not available")
+    b.build()
+    src = os.path.join(os.path.dirname(b.SO_PATH), "csrc", "api.cu")
+    now = time.time() + 2
+    os.utime(src, (now, now))                                   # sources newer than the library
+    code = "import sys; sys.path.insert(0, %r); from nvdiffrast_b200 import _lib; l = _lib.load(); print(len(_lib.SIGNATURES))" % ROOT
+    procs = [subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for _ in range(2)]
+    outs = [p.communicate(timeout=900) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-2000:]
+        assert int(o.strip().splitlines()[-1]) > 10
+    assert not b.needs_build()
