@@ -276,7 +276,9 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_grad_kernel(const Inte
 #define IPF_UNROLL_DA 2
 #endif
 // backward (r02 call 13, same box): 4 groups in flight at <= 64 registers (4 CTAs/SM) against 2 groups unconstrained: A = 3 target
-// 0.710 -> 0.677 ms, c2 0.509 -> 0.482, c3 op-by-op (A = 2 + differentials) 0.846 -> 0.808; 3 groups: 0.690 / 0.487 / 0.817
+// 0.710 -> 0.677 ms, c2 0.509 -> 0.482, c3 op-by-op (A = 2 + differentials) 0.846 -> 0.808; 3 groups: 0.690 / 0.487 / 0.817.
+// call 18, A = 3 target: 6 groups 0.859, 8 groups at 3 CTAs 1.168 (code size), 5 CTAs/SM 0.668, dy requested for all groups
+// before the first group's gathers 0.699 -> none adopted
 #ifndef IPG_UNROLL_PLAIN
 #define IPG_UNROLL_PLAIN 4
 #endif
@@ -379,9 +381,6 @@ __global__ void __launch_bounds__(IP_THREADS) interpolate_fwd_fast(const InterpP
 // go through pm::raster_grad instead of memory, and the vertex-position gradients are summed over the same triangle runs.
 // r02 call 14 (c2 / c4 fused kernel): 4 CTAs/SM at 64 registers 0.638 / 0.715 ms; 3 CTAs at 80 registers 0.810 / 0.767; 2 CTAs the same
 // call 15: 2 groups in flight instead of 4 (half the code: ncu showed instruction-fetch stalls) 0.593 / 0.632; 5 CTAs/SM 0.607 / 0.749
-#ifndef IPG_EARLY_DY
-#define IPG_EARLY_DY 0
-#endif
 #ifndef IPC_MINB
 #define IPC_MINB 4
 #endif
@@ -430,20 +429,6 @@ __global__ void __launch_bounds__(IP_THREADS, RASTER ? IPC_MINB : (DA ? IPG_MINB
             r[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (inb[u]) r[u] = ld_stream_f4((const float4*)p.rast + img + px);
         }
-#if IPG_EARLY_DY
-        // dy of every group in flight is requested as soon as its rast line shows geometry (a non-zero triangle id), before the
-        // first group's triangle -> vertex gathers start: one more level of loads in flight per warp
-        AosRaw<A> rawdy[IPG_UNROLL];
-        #pragma unroll
-        for (int u = 0; u < IPG_UNROLL; u++)
-        {
-            const int g = g0 + u * wstride;
-            const bool geo = inb[u] && r[u].w != 0.f;
-            rawdy[u].q[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g < groups && __any_sync(0xffffffffu, geo))             // warp-uniform
-                warp_load_aos_issue<A>(p.dy + (img + (size_t)g * 32) * A, rawdy[u], lane, (SK == 1) ? geo : inb[u], row_aligned && (g * 32 + 32 <= hw));
-        }
-#endif
         #pragma unroll
         for (int u = 0; u < IPG_UNROLL; u++)
         {
@@ -464,12 +449,7 @@ __global__ void __launch_bounds__(IP_THREADS, RASTER ? IPC_MINB : (DA ? IPG_MINB
                 for (int i = 0; i < (DA ? 2 * A : 1); i++) dda[i] = 0.f;
                 float4 db = make_float4(0.f, 0.f, 0.f, 0.f);
                 // K = 3 / 6 go through the warp transpose (all lanes take part); vector widths are fetched only under geometry
-#if IPG_EARLY_DY
-                warp_load_aos_finish<A>(p.dy + pbase * A, rawdy[u], dy, lane, (SK == 1) ? valid : inb[u], full, sw);
-                if (SK == 1 && !valid) { _Pragma("unroll") for (int i = 0; i < A; i++) dy[i] = 0.f; }
-#else
                 warp_load_aos<A>(p.dy + pbase * A, dy, lane, (SK == 1) ? valid : inb[u], full, sw);
-#endif
                 if (DA)
                 {
                     warp_load_aos<(DA ? 2 * A : 1)>(p.dda + pbase * (2 * A), dda, lane, (SK == 1) ? valid : inb[u], full, sw);
