@@ -37,7 +37,7 @@ def _run(cfg, n, res, tex_res=1024):
     rep = json.loads(r.stdout.strip().splitlines()[-1])
     out = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out):
-        with open(os.path.join(out, "grad_parity_%s.json" % cfg), "w") as f:
+        with open(os.path.join(out, "grad_parity_%s_%dx%d.json" % (cfg, n, res)), "w") as f:     # the small-size chain test reuses _run
             json.dump(rep, f, indent=1)
     return rep
 
