@@ -1036,6 +1036,7 @@ struct ChainParams
     float* g_rast; float* g_rast_db;                    // !RASTER
     int Va, V, T, attr_per_image, grad_db;
     float xs, xo, ys, yo;
+    unsigned* strip_counter;                            // STRIPS schedule: zeroed work counter (tail of the scratch buffer)
 };
 
 // uv = b0 a0 + b1 a1 + b2 a2 and its screen-space derivatives: the expressions of interpolate_fwd_fast (A = 2, all
@@ -1059,8 +1060,22 @@ static __device__ __forceinline__ void interp_uv(float4 r, float4 db, const floa
 #ifndef TCG_MINB
 #define TCG_MINB 5          // <= 102 registers: 20 warps per SM (measured 2.72 -> 2.39 ms against 4 CTAs at 118 registers; 3 CTAs: 2.82)
 #endif
+// Work schedule of the fused kernel.  0: grid-stride over the flat array of 32-pixel groups (a warp's consecutive groups lie
+// gridDim * 128 pixels apart).  1: STRIPS -- a warp takes 32-pixel-wide, TCG_STRIP_ROWS-high strips from a global work counter
+// and walks them top to bottom: vertically adjacent groups share their triangles and texel quads (index / vertex / texel
+// gathers hit L1 instead of L2), the pixel coordinates need no division, and the counter balances background against
+// geometry exactly instead of statistically.  Needs W % 32 == 0 and H % TCG_STRIP_ROWS == 0 (otherwise schedule 0).
+#ifndef TCG_STRIPS
+#define TCG_STRIPS 0
+#endif
+#ifndef TCG_STRIP_ROWS
+#define TCG_STRIP_ROWS 8
+#endif
+#ifndef TCG_STRIP_WAVES
+#define TCG_STRIP_WAVES 1   // CTAs launched per resident CTA slot (1 = persistent grid)
+#endif
 
-template <int C, int F, int B, bool RASTER>
+template <int C, int F, int B, bool RASTER, bool STRIPS>
 __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fast(const TexParams p, const ChainParams q)
 {
     const TexMode m = tex_mode_static<F, B>(p);
@@ -1073,22 +1088,21 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
     const size_t groups = (total + 31) >> 5;
     const size_t wstride = (size_t)gridDim.x * (TEXG_THREADS / 32);
     const bool trilinear = (m.filter == B200DR_FILTER_LINEAR_MIPMAP_LINEAR);
+    const size_t NO_GROUP = ~(size_t)0;
     Pending<C> pd;
     pd.level = -1; pd.tc = make_int4(-1, -1, -1, -1); pd.fu = 0.f; pd.fv = 0.f; pd.w = make_float4(0.f, 0.f, 0.f, 0.f);
     #pragma unroll
     for (int i = 0; i < C; i++) pd.sum[i] = 0.f;
     bool cached = false;
 
-    // image / in-image offset of the warp's current group, advanced incrementally (no 64-bit division per pixel); hw < 2^30
-    size_t g = (size_t)blockIdx.x * (TEXG_THREADS / 32) + warp;
-    int n0 = (int)((g * 32) / hw);
-    unsigned r0 = (unsigned)(g * 32 - (size_t)n0 * hw);
-    const unsigned hw32 = (unsigned)hw;
-    for (; g < groups; g += wstride)
+    // One 32-pixel group: g = group index in the flat pixel array, n = image of lane 0 .. (n + 1 when the group straddles two
+    // images, schedule 0 only), rl = this lane's pixel index inside its image, (px, py) = its coordinates (STRIPS only), gn = the
+    // group this warp will process next (L2 prefetch) or NO_GROUP.
+    auto process = [&](const size_t g, const int n, const unsigned rl, const unsigned px_, const unsigned py_, const size_t gn)
     {
         TexGradIn<C> in;
         in.g = g; in.pidx = g * 32 + lane;
-        in.inb = in.pidx < total; in.full = (g * 32 + 32 <= total);
+        in.inb = STRIPS ? true : (in.pidx < total); in.full = STRIPS ? true : (g * 32 + 32 <= total);
         in.bias = 0.f;
         const size_t pidx = in.pidx;
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1096,8 +1110,7 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
         warp_load_aos_issue<C>(p.dy + g * 32 * C, in.dy, lane, in.inb, in.full);
         {   // this warp's next group: one prefetch.global.L2 per lane and tensor (LSU path; measured -5 % on this kernel, whose
             // iterations are long enough for the lines to arrive; the bulk / TMA form and the short-iteration kernels lose)
-            const size_t gn = g + wstride;
-            if (gn * 32 + 32 <= total)
+            if (STRIPS ? (gn != NO_GROUP) : (gn * 32 + 32 <= total))
             {
                 asm volatile("prefetch.global.L2 [%0];" :: "l"((const float4*)q.rast + gn * 32 + lane) : "memory");
                 if (lane * 16 < 32 * C * 4) asm volatile("prefetch.global.L2 [%0];" :: "l"((const char*)(p.dy + gn * 32 * C) + lane * 16) : "memory");
@@ -1105,14 +1118,6 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
         }
 
         // ---- triangle of the pixel, attribute rows, recomputed texture coordinates
-        unsigned rl = r0 + (unsigned)lane;              // pixel index inside image n
-        int n = n0;
-        if (rl >= hw32) { rl -= hw32; n++; }
-        {   // advance the warp's (image, offset) to its next group
-            size_t adv = (size_t)r0 + wstride * 32;
-            while (adv >= hw) { adv -= hw; n0++; }
-            r0 = (unsigned)adv;
-        }
         int triIdx = in.inb ? float_to_triidx(r.w) - 1 : -1;
         if (triIdx >= q.T) triIdx = -1;
         int ai0 = 0, ai1 = 0, ai2 = 0, vi0 = 0, vi1 = 0, vi2 = 0;
@@ -1151,7 +1156,7 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
                 st_stream_f4((float4*)q.g_rast + pidx, make_float4(0.f, 0.f, 0.f, 0.f));
                 if (q.g_rast_db) st_stream_f4((float4*)q.g_rast_db + pidx, make_float4(0.f, 0.f, 0.f, 0.f));
             }
-            continue;
+            return;
         }
 
         // ---- interpolate backward (A = 2, all differentials): csrc/common/interpolate.cu:131-274 restated for registers
@@ -1192,7 +1197,7 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
                 st_stream_f4((float4*)q.g_rast + pidx, valid ? make_float4(gr.x, gr.y, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f));
                 if (q.g_rast_db) st_stream_f4((float4*)q.g_rast_db + pidx, valid ? gdb : make_float4(0.f, 0.f, 0.f, 0.f));
             }
-            continue;
+            return;
         }
 
         // ---- rasterize backward: pm::raster_grad on (g_rast.xy, g_rast_db), one 128-bit reduction per vertex and triangle run
@@ -1210,7 +1215,7 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
             if (pv)
             {
                 const float4* vb = (const float4*)q.pos + (size_t)n * q.V;
-                const unsigned py = rl / (unsigned)p.W, px = rl - py * (unsigned)p.W;
+                const unsigned py = STRIPS ? py_ : rl / (unsigned)p.W, px = STRIPS ? px_ : rl - py * (unsigned)p.W;
                 const float fx = q.xs * (float)px + q.xo, fy = q.ys * (float)py + q.yo;
                 pm::PixelTri t;
                 pm::pixel_tri(t, __ldg(vb + vi0), __ldg(vb + vi1), __ldg(vb + vi2), fx, fy);
@@ -1230,6 +1235,55 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
                 red_add4(gp + 4 * vi1, make_float4(gv9[3], gv9[4], 0.f, gv9[5]));
                 red_add4(gp + 4 * vi2, make_float4(gv9[6], gv9[7], 0.f, gv9[8]));
             }
+        }
+    };
+
+    if (STRIPS)
+    {
+        // strip s = (image, strip row, strip column); the warp holds its current strip and the one after it (whose first
+        // group is the prefetch target of the current strip's last row)
+        const unsigned gpr = (unsigned)p.W >> 5, spi = gpr * ((unsigned)p.H / TCG_STRIP_ROWS), nstrips = spi * (unsigned)p.N;
+        auto grab = [&]() { unsigned s = 0; if (lane == 0) s = atomicAdd(q.strip_counter, 1u); return __shfl_sync(0xffffffffu, s, 0); };
+        unsigned cur = grab();
+        while (cur < nstrips)                           // warp-uniform
+        {
+            const unsigned nxt = grab();
+            const unsigned n = cur / spi, rem = cur - n * spi, sy = rem / gpr, sx = rem - sy * gpr;
+            unsigned g_nxt = 0xffffffffu;                // group indices fit 32 bits on this path (checked by the host code)
+            if (nxt < nstrips)
+            {
+                const unsigned n2 = nxt / spi, rem2 = nxt - n2 * spi, sy2 = rem2 / gpr, sx2 = rem2 - sy2 * gpr;
+                g_nxt = (n2 * (unsigned)p.H + sy2 * TCG_STRIP_ROWS) * gpr + sx2;
+            }
+            const unsigned y0 = sy * TCG_STRIP_ROWS, px = sx * 32 + (unsigned)lane;
+            const unsigned g0 = (n * (unsigned)p.H + y0) * gpr + sx;
+            #pragma unroll 1
+            for (unsigned row = 0; row < TCG_STRIP_ROWS; row++)
+            {
+                const unsigned g = g0 + row * gpr, gn = (row + 1 < TCG_STRIP_ROWS) ? g + gpr : g_nxt;
+                process((size_t)g, (int)n, (y0 + row) * (unsigned)p.W + px, px, y0 + row, gn == 0xffffffffu ? NO_GROUP : (size_t)gn);
+            }
+            cur = nxt;
+        }
+    }
+    else
+    {
+        // image / in-image offset of the warp's current group, advanced incrementally (no 64-bit division per pixel); hw < 2^30
+        size_t g = (size_t)blockIdx.x * (TEXG_THREADS / 32) + warp;
+        int n0 = (int)((g * 32) / hw);
+        unsigned r0 = (unsigned)(g * 32 - (size_t)n0 * hw);
+        const unsigned hw32 = (unsigned)hw;
+        for (; g < groups; g += wstride)
+        {
+            unsigned rl = r0 + (unsigned)lane;          // pixel index inside image n
+            int n = n0;
+            if (rl >= hw32) { rl -= hw32; n++; }
+            {   // advance the warp's (image, offset) to its next group
+                size_t adv = (size_t)r0 + wstride * 32;
+                while (adv >= hw) { adv -= hw; n0++; }
+                r0 = (unsigned)adv;
+            }
+            process(g, n, rl, 0u, 0u, g + wstride);
         }
     }
     pending_flush<C>(pd, p, lane);
@@ -1993,7 +2047,9 @@ extern "C" int b200dr_texture_fwd(const float* tex, const float* const* mip_ptrs
     return 0;
 }
 
-// Bytes of the channel-padded gradient pyramid used by b200dr_texture_grad (levels 0..max_level).
+// Bytes of the channel-padded gradient pyramid used by b200dr_texture_grad (levels 0..max_level), followed by a
+// TEXG_TAIL_BYTES tail of kernel bookkeeping (the fused chain backward's work counter); all of it is zeroed by the op.
+#define TEXG_TAIL_BYTES 256
 extern "C" size_t b200dr_texture_grad_scratch_bytes(int texD, int texH, int texW, int C, int max_level)
 {
     size_t Cp = (size_t)((C + 3) & ~3), total = 0;
@@ -2002,7 +2058,7 @@ extern "C" size_t b200dr_texture_grad_scratch_bytes(int texD, int texH, int texW
         size_t w = (texW >> L) > 1 ? (texW >> L) : 1, h = (texH >> L) > 1 ? (texH >> L) : 1;
         total += w * h * texD * Cp * sizeof(float);
     }
-    return total;
+    return total + TEXG_TAIL_BYTES;
 }
 
 extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptrs, int max_level,
@@ -2096,23 +2152,23 @@ extern "C" int b200dr_texture_grad(const float* tex, const float* const* mip_ptr
     return 0;
 }
 
-template <int F, int B, bool RASTER>
+template <int F, int B, bool RASTER, bool STRIPS>
 static void launch_chain_grad_c(const TexParams& p, const ChainParams& q, unsigned blocks, cudaStream_t stream)
 {
     switch (p.C) {
-    case 1: texture_chain_grad_fast<1, F, B, RASTER><<<blocks, TEXG_THREADS, 0, stream>>>(p, q); break;
-    case 2: texture_chain_grad_fast<2, F, B, RASTER><<<blocks, TEXG_THREADS, 0, stream>>>(p, q); break;
-    case 3: texture_chain_grad_fast<3, F, B, RASTER><<<blocks, TEXG_THREADS, 0, stream>>>(p, q); break;
-    case 4: texture_chain_grad_fast<4, F, B, RASTER><<<blocks, TEXG_THREADS, 0, stream>>>(p, q); break;
+    case 1: texture_chain_grad_fast<1, F, B, RASTER, STRIPS><<<blocks, TEXG_THREADS, 0, stream>>>(p, q); break;
+    case 2: texture_chain_grad_fast<2, F, B, RASTER, STRIPS><<<blocks, TEXG_THREADS, 0, stream>>>(p, q); break;
+    case 3: texture_chain_grad_fast<3, F, B, RASTER, STRIPS><<<blocks, TEXG_THREADS, 0, stream>>>(p, q); break;
+    case 4: texture_chain_grad_fast<4, F, B, RASTER, STRIPS><<<blocks, TEXG_THREADS, 0, stream>>>(p, q); break;
     }
 }
-template <bool RASTER>
+template <bool RASTER, bool STRIPS>
 static void launch_chain_grad(const TexParams& p, const ChainParams& q, unsigned blocks, cudaStream_t stream)
 {
     const int f = p.filter, b = p.boundary;
-    if      (f == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && b == B200DR_BOUNDARY_WRAP)  launch_chain_grad_c<B200DR_FILTER_LINEAR_MIPMAP_LINEAR, B200DR_BOUNDARY_WRAP, RASTER>(p, q, blocks, stream);
-    else if (f == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && b == B200DR_BOUNDARY_CLAMP) launch_chain_grad_c<B200DR_FILTER_LINEAR_MIPMAP_LINEAR, B200DR_BOUNDARY_CLAMP, RASTER>(p, q, blocks, stream);
-    else                                                                            launch_chain_grad_c<-1, -1, RASTER>(p, q, blocks, stream);
+    if      (f == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && b == B200DR_BOUNDARY_WRAP)  launch_chain_grad_c<B200DR_FILTER_LINEAR_MIPMAP_LINEAR, B200DR_BOUNDARY_WRAP, RASTER, STRIPS>(p, q, blocks, stream);
+    else if (f == B200DR_FILTER_LINEAR_MIPMAP_LINEAR && b == B200DR_BOUNDARY_CLAMP) launch_chain_grad_c<B200DR_FILTER_LINEAR_MIPMAP_LINEAR, B200DR_BOUNDARY_CLAMP, RASTER, STRIPS>(p, q, blocks, stream);
+    else                                                                            launch_chain_grad_c<-1, -1, RASTER, STRIPS>(p, q, blocks, stream);
 }
 
 // Fused backward of texture(interpolate(attr, rasterize(pos))): see texture_chain_grad_fast.  Extension of the op surface (the
@@ -2166,9 +2222,25 @@ extern "C" int b200dr_texture_chain_grad(const float* tex, const float* const* m
     size_t groups = ((size_t)N * H * W + 31) / 32;
     size_t blocks = (groups + (TEXG_THREADS / 32) - 1) / (TEXG_THREADS / 32);
     size_t bcap = (size_t)b200dr_num_sms() * TCG_MINB * 4;
-    if (blocks > bcap) blocks = b200dr_balanced_blocks(bcap, TEXG_THREADS / 32, W);
-    if (pos) launch_chain_grad<true>(p, q, (unsigned)blocks, stream);
-    else     launch_chain_grad<false>(p, q, (unsigned)blocks, stream);
+    q.strip_counter = (unsigned*)((char*)scratch + need - TEXG_TAIL_BYTES);
+    const bool strips = TCG_STRIPS && (W % 32) == 0 && (H % TCG_STRIP_ROWS) == 0 && groups < 0xffffffffu;
+    if (strips)
+    {
+        size_t nstrips = groups / TCG_STRIP_ROWS;
+        blocks = (nstrips + (TEXG_THREADS / 32) - 1) / (TEXG_THREADS / 32);
+        bcap = (size_t)b200dr_num_sms() * TCG_MINB * TCG_STRIP_WAVES;   // persistent: the work counter balances, no stride to choose
+        if (blocks > bcap) blocks = bcap;
+#if TCG_STRIPS
+        if (pos) launch_chain_grad<true, true>(p, q, (unsigned)blocks, stream);
+        else     launch_chain_grad<false, true>(p, q, (unsigned)blocks, stream);
+#endif
+    }
+    else
+    {
+        if (blocks > bcap) blocks = b200dr_balanced_blocks(bcap, TEXG_THREADS / 32, W);
+        if (pos) launch_chain_grad<true, false>(p, q, (unsigned)blocks, stream);
+        else     launch_chain_grad<false, false>(p, q, (unsigned)blocks, stream);
+    }
     B200DR_CHECK_LAUNCH(fn);
 
     r.C = C; r.Cp = p.Cp; r.texD = texD; r.mip_max = p.mip_max; r.baseW = texW; r.baseH = texH;
