@@ -557,8 +557,70 @@ def envphong_shaped(mod, device, peak, n_img=4, res=1024, face=512, C=3):
             "ops": {k: {"ms": v["ms"], "bytes_per_pixel": nbytes["b200dr_" + k] // P, "frac": v.get("frac")} for k, v in table.items() if "frac" in v}}
 
 
+def graph_leg(res=256, n_img=1, tex_res=256):
+    """Launch-bound regime (a fitting loop at low resolution): the same full chain, eager vs replayed from ONE CUDA graph
+    (nvdiffrast_b200/graphs.py).  Timed with CUDA events around 100 eager steps / 300 replays after warm-up; inputs stay on
+    the device (the regime of interest is the per-step launch cost, not the copies)."""
+    import nvdiffrast_b200.torch as dr
+    from nvdiffrast_b200 import graphs
+    device = torch.device("cuda", 0)
+    c = wl.config_c3(n=n_img, res=res, tex_res=tex_res)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    ctx = dr.RasterizeCudaContext(device)
+    tri, uv_idx = t(c["tri"]), t(c["uv_idx"])
+    topo = dr.antialias_construct_topology_hash(tri)
+    pos = t(c["pos"]).requires_grad_(True); uv = t(c["uv"]).requires_grad_(True); tex = t(c["tex"]).requires_grad_(True)
+    dy = torch.randn((n_img, res, res, 3), device=device, generator=torch.Generator(device=device).manual_seed(2))
+
+    def step():
+        rast, db = dr.rasterize(ctx, pos, tri, c["res"])
+        texc, texd = dr.interpolate(uv[None], rast, uv_idx, rast_db=db, diff_attrs="all")
+        color = dr.texture(tex, texc, texd, filter_mode="linear-mipmap-linear", max_mip_level=7)
+        out = dr.antialias(color, rast, pos, tri, topology_hash=topo)
+        return torch.autograd.grad(out, [pos, uv, tex], dy)
+
+    def timed(fn, iters):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record(); e1.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    eager_ms = timed(step, 100)
+    captured = graphs.capture(step)
+    graph_ms = timed(captured.replay, 300)
+    g_eager = step(); g_graph = captured.replay()
+    torch.cuda.synchronize()
+    err = max(float((a - b).abs().max()) / max(float(a.abs().max()), 1e-30) for a, b in zip(g_eager, g_graph))
+    P = n_img * res * res
+    return {"workload": "full chain fwd+bwd, 5856-triangle mesh, %d^2, %d image(s), texture %d^2: launch-bound" % (res, n_img, tex_res),
+            "eager_ms_per_step": eager_ms, "graph_ms_per_step": graph_ms, "speedup": eager_ms / graph_ms,
+            "graph_Mpixel_per_s": P / (graph_ms * 1e-3) / 1e6, "max_rel_grad_diff_graph_vs_eager": err}
+
+
+def graph_leg_subprocess(timeout=180):
+    """Own process: a failed capture can leave the CUDA context unusable, and must not take the bench line with it."""
+    import subprocess
+    try:
+        pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--graph-leg"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                            text=True, timeout=timeout, cwd=ROOT)
+        lines = [l for l in pr.stdout.splitlines() if l.startswith("{")]
+        if pr.returncode != 0 or not lines:
+            return {"error": (pr.stderr or "no output").strip().splitlines()[-1][:300]}
+        return json.loads(lines[-1])
+    except Exception as e:      # timeout, JSON error: report, never fail the bench line
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+
 def main():
     claim_stdout()
+    if "--graph-leg" in sys.argv:
+        emit(graph_leg())
+        return
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -685,6 +747,7 @@ def main():
             out["target_kernels"] = target_kernels(mod, device, peak)
             out["other_configs"] = {name: side_config(mod, name, K, W, device, peak) for name in ("c2", "c4", "c5")}
             out["other_configs"]["envphong_shaped"] = envphong_shaped(mod, device, peak)
+            out["other_configs"]["cuda_graph_launch_bound"] = graph_leg_subprocess()
     if not args.no_cpu_baseline and world == 1:
         ns = {"c3": 12, "c5": 12, "c2": 16, "c4": 1}[workload]       # bounded sample: ~10 s of host time
         rate, dt, thr = cpu_oracle_rate(workload, res, ns)
