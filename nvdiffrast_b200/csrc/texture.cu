@@ -1071,6 +1071,12 @@ static __device__ __forceinline__ void interp_uv(float4 r, float4 db, const floa
 #ifndef TCG_STRIP_ROWS
 #define TCG_STRIP_ROWS 8
 #endif
+#ifndef TCG_PF_DB
+#define TCG_PF_DB 0         // L2 prefetch of the next group's rast_db line as well
+#endif
+#ifndef TCG_EARLY_DB
+#define TCG_EARLY_DB 0      // request rast_db with the index gathers instead of after their validity test
+#endif
 #ifndef TCG_STRIP_WAVES
 #define TCG_STRIP_WAVES 1   // CTAs launched per resident CTA slot (1 = persistent grid)
 #endif
@@ -1114,6 +1120,11 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
             {
                 asm volatile("prefetch.global.L2 [%0];" :: "l"((const float4*)q.rast + gn * 32 + lane) : "memory");
                 if (lane * 16 < 32 * C * 4) asm volatile("prefetch.global.L2 [%0];" :: "l"((const char*)(p.dy + gn * 32 * C) + lane * 16) : "memory");
+#if TCG_PF_DB
+                // rast_db is read under geometry only, AFTER the index gathers have been checked: without this its DRAM latency is
+                // paid in series with theirs (background groups waste the 512 bytes; DRAM runs at 15 % in this kernel)
+                if (q.rast_db) asm volatile("prefetch.global.L2 [%0];" :: "l"((const float4*)q.rast_db + gn * 32 + lane) : "memory");
+#endif
             }
         }
 
@@ -1121,6 +1132,11 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
         int triIdx = in.inb ? float_to_triidx(r.w) - 1 : -1;
         if (triIdx >= q.T) triIdx = -1;
         int ai0 = 0, ai1 = 0, ai2 = 0, vi0 = 0, vi1 = 0, vi2 = 0;
+#if TCG_EARLY_DB
+        // requested together with the index gathers (it only needs the coverage bit), not after their validity test
+        float4 db_early = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (triIdx >= 0 && q.rast_db) db_early = ld_stream_f4((const float4*)q.rast_db + pidx);
+#endif
         if (triIdx >= 0)
         {
             ai0 = __ldg(q.attr_tri + triIdx * 3); ai1 = __ldg(q.attr_tri + triIdx * 3 + 1); ai2 = __ldg(q.attr_tri + triIdx * 3 + 2);
@@ -1137,7 +1153,11 @@ __global__ void __launch_bounds__(TEXG_THREADS, TCG_MINB) texture_chain_grad_fas
         in.uv = make_float2(0.f, 0.f); in.da = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid)
         {
+#if !TCG_EARLY_DB
             if (q.rast_db) db = ld_stream_f4((const float4*)q.rast_db + pidx);
+#else
+            db = db_early;
+#endif
             float2 t;
             t = __ldg((const float2*)q.attr + aoff + ai0); a0[0] = t.x; a0[1] = t.y;
             t = __ldg((const float2*)q.attr + aoff + ai1); a1[0] = t.x; a1[1] = t.y;
