@@ -1066,16 +1066,16 @@ static __device__ __forceinline__ void interp_uv(float4 r, float4 db, const floa
 // gathers hit L1 instead of L2), the pixel coordinates need no division, and the counter balances background against
 // geometry exactly instead of statistically.  Needs W % 32 == 0 and H % TCG_STRIP_ROWS == 0 (otherwise schedule 0).
 #ifndef TCG_STRIPS
-#define TCG_STRIPS 0
+#define TCG_STRIPS 1
 #endif
 #ifndef TCG_STRIP_ROWS
 #define TCG_STRIP_ROWS 8
 #endif
 #ifndef TCG_PF_DB
-#define TCG_PF_DB 0         // L2 prefetch of the next group's rast_db line as well
+#define TCG_PF_DB 1         // L2 prefetch of the next group's rast_db line as well
 #endif
 #ifndef TCG_EARLY_DB
-#define TCG_EARLY_DB 0      // request rast_db with the index gathers instead of after their validity test
+#define TCG_EARLY_DB 1      // request rast_db with the index gathers instead of after their validity test
 #endif
 #ifndef TCG_STRIP_WAVES
 #define TCG_STRIP_WAVES 1   // CTAs launched per resident CTA slot (1 = persistent grid)
