@@ -153,7 +153,7 @@ int b200dr_texture_fwd(const float* tex, const float* const* mip_ptrs, int max_l
 
 /* Replaces texture_grad_{nearest,linear,linear_mipmap_nearest,linear_mipmap_linear}
  * (torch_texture.cpp:421-716, texture_kernel.cu:843-1154).
- *   scratch: b200dr_texture_grad_scratch_bytes() bytes (channel-padded gradient pyramid, zeroed here).
+ *   scratch: b200dr_texture_grad_scratch_bytes() bytes (channel-padded gradient pyramid + a 256-byte bookkeeping tail, zeroed here).
  *   tex / mip_ptrs: padded levels as in b200dr_texture_fwd.  g_tex (UNPADDED, shape of the user's tex) is fully written.  pull_mips != 0 (internal mip stack): mip-level gradients are pulled
  *   down into g_tex and g_mip_ptrs is ignored; pull_mips == 0 with max_level > 0 (custom mip stack): level l's
  *   gradient is written, UNPADDED, to g_mip_ptrs[l] (1..max_level).
