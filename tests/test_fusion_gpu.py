@@ -122,13 +122,6 @@ def test_fused_chain_modes(dr, ctx, c3, kw):
     _compare(dr, ctx, c3, 2, **kw)
 
 
-@pytest.mark.parametrize("res", [100, 72])
-def test_fused_chain_ragged_resolutions(dr, ctx, res):
-    """Widths that are not a multiple of 32: the fused kernel leaves its strip schedule (32 x 8 pixel strips from a work counter) for
-    the grid-stride loop over the flat pixel array, whose 32-pixel groups straddle rows and images."""
-    _compare(dr, ctx, wl.config_c3(n=3, res=res, tex_res=64), 3)
-
-
 @pytest.mark.parametrize("need", [("pos",), ("uv",), ("tex",), ("pos", "tex"), ("uv", "tex")])
 def test_fused_chain_partial_gradients(dr, ctx, c3, need):
     # only the texture needs a gradient: nothing flows past the texture op, so the intermediates carry no provenance and the
