@@ -716,6 +716,11 @@ def main():
                            "frac": ach / peak, "traffic": (tr["dram_bytes_per_pixel"] * P if tr else None),
                            "traffic_source": (tr.get("source") if tr else None), "peak_source": peak_src,
                            "algorithmic_bytes_per_launch": nbytes[dom], "avg_launch_ms": avg}
+        if dom == "b200dr_texture_chain_grad":
+            # what the HBM fraction of this kernel means: the fusion removed 152 of the 196 B/px its three ops moved, the arithmetic stayed
+            out["roofline"]["note"] = ("fused texture+interpolate+rasterize backward: bound by instruction issue, not HBM (ncu, "
+                                       "profiles/r02_ncu_chain_grad_strips.md: 638 warp-instructions per 32 pixels, issue slots 68 % busy at the "
+                                       "20 warps/SM its 96 registers allow, DRAM 21 %); the three ops it replaces take 2.95 ms for the same work")
         chain_bytes = sum(nbytes[n] * ops[n][1] / Kt for n in ops if n in nbytes)
         out["chain_roofline"] = {"algorithmic_bytes_per_step": chain_bytes, "achieved_GBps": chain_bytes / (ms_step * 1e-3) / 1e9,
                                  "frac": chain_bytes / (ms_step * 1e-3) / 1e9 / peak}
