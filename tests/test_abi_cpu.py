@@ -46,6 +46,10 @@ def test_host_side_helpers_without_gpu():
     assert lib.b200dr_rasterize_pick_path(8, 1000000, 2048, 2048) == 2
     assert lib.b200dr_rasterize_scratch_bytes(8, 1000000, 2048, 2048, 2) == 8 * 2048 * 2048 * 8
     assert lib.b200dr_rasterize_scratch_bytes(1, 12, 64, 64, 1) >= 7 * 12 * 40
+    # texture-gradient scratch: channel-padded pyramid (levels 0..max) + the 256-byte bookkeeping tail (strip counter of the fused backward)
+    assert lib.b200dr_texture_grad_scratch_bytes(1, 4, 8, 3, 0) == 4 * 8 * 4 * 4 + 256
+    assert lib.b200dr_texture_grad_scratch_bytes(2, 4, 4, 5, 2) == 2 * 8 * 4 * (16 + 4 + 1) + 256
+    assert lib.b200dr_texture_grad_scratch_bytes(1, 1024, 1024, 3, 9) % 16 == 0
     # mip layout matches the oracle's restatement of calculateMipInfo
     import oracle
     for shape, limit in [((1, 1024, 1024, 3), -1), ((2, 16, 64, 4), -1), ((1, 32, 32, 1), 3), ((1, 1, 8, 2), -1)]:
